@@ -1,0 +1,879 @@
+// mmc_api.cu -- host orchestration behind the C ABI of include/minimod_cuda.h.
+//
+// One context == one CUDA device.  Batches move through `n_slots` staging slots, each with
+// pinned host arrays, an HBM mirror and its own stream, so the H2D copy of batch i+1
+// overlaps the kernels of batch i (this is what replaces the reference's
+// load || process || merge pthread pipeline, src/freq_main.c:404-474, and the per-batch
+// worker pool of src/thread.c:100-158).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/minimod_cuda.h"
+#include "mmc_device.cuh"
+
+using namespace mmc;
+
+static_assert(sizeof(FreqRecDev) == sizeof(mmc_freq_rec_t), "record layout");
+static_assert(sizeof(FreqRecDev) == 24, "record size");
+
+namespace {
+
+constexpr size_t kSlack = 64;                 // readable bytes after the last slice of a pool
+constexpr uint32_t kTileCells = 8192;         // cells per finalize tile
+constexpr uint32_t kExcCap = 1u << 22;        // exception-run starts per contig
+
+std::string g_create_error;
+
+struct Slot {
+    mmc_batch_t pub;
+    // host (pinned) and device arenas share one layout; offsets in bytes
+    uint8_t *h_arena = nullptr, *d_arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t o_tid, o_pos, o_lseq, o_ncig, o_mmlen, o_mllen, o_cigoff, o_seqoff, o_mmoff, o_mloff, o_flag, o_hp;
+    size_t o_cigar, o_seq, o_mm, o_ml;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    // small device state: [0] err (u64), [1] view_n (u64), [2] work counter (u32)
+    unsigned long long *d_state = nullptr;
+    unsigned long long *h_state = nullptr;     // pinned mirror
+    ViewDev *d_view = nullptr;
+    uint32_t *d_scratch = nullptr;
+    size_t scratch_words = 0;
+    std::vector<mmc_view_rec_t> view_out;
+    bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false;
+    uint32_t n_reads_submitted = 0;
+};
+
+struct ContigHost {
+    std::string name;
+    uint32_t len = 0;
+    ContigDev dev{};
+    uint32_t *d_exc_start = nullptr;
+    uint8_t *d_exc_letter = nullptr;
+    bool loaded = false;
+};
+
+}  // namespace
+
+struct mmc_ctx {
+    mmc_opts_t opts{};
+    std::vector<mmc_mod_t> mods;
+    std::vector<ContigHost> contigs;
+    std::vector<Slot> slots;
+    std::string err;
+    int sm_count = 0, ctas_per_sm = 1, threads = 128;
+    int n_code_slots = 1, n_hap_slots = 1, wild_req = -1;
+    ReqMod *d_req = nullptr;
+    unsigned long long *d_code_keys = nullptr;
+    ContigDev *d_contigs = nullptr;
+    int32_t *d_touch = nullptr;                // [2*n_contigs]: lo then hi
+    SparseRec *d_sparse = nullptr;
+    unsigned long long *d_sparse_n = nullptr;
+    uint64_t sparse_cap = 0, view_cap = 0;
+    bool committed = false;
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr;
+    // ref-pack staging
+    uint8_t *d_ascii = nullptr; size_t ascii_cap = 0;
+    uint32_t *d_exc_tmp_start = nullptr; uint8_t *d_exc_tmp_letter = nullptr; uint32_t *d_exc_n = nullptr;
+    // results
+    std::vector<mmc_freq_rec_t> freq_out;
+    std::vector<std::string> code_names;
+    mmc_timers_t tm{};
+    int32_t cig_smem_cap = kCigSmem, bitmap_smem_words = kBitmapWords, idx_smem_cap = kIdxSmem;
+};
+
+namespace {
+
+int fail(mmc_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(ctx, MMC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+unsigned long long pack_code(const char *s) {
+    unsigned long long k = 0;
+    for (int i = 0; i < 8 && s[i]; ++i) k |= (unsigned long long)(uint8_t)s[i] << (8 * i);
+    return k;
+}
+
+std::string unpack_code(unsigned long long k) {
+    std::string s;
+    for (int i = 0; i < 8; ++i) {
+        char c = (char)((k >> (8 * i)) & 0xff);
+        if (!c) break;
+        s.push_back(c);
+    }
+    return s;
+}
+
+const char *read_error_text(uint32_t code) {
+    switch (code) {
+    case kErrHardClip: return "Hard clipping found and they are not supported.\nTry following workarounds.\n\t01. Filter out non-primary alignments\n\t\tsamtools view -h -F 2308 reads.bam -o primary_reads.bam\n\t02. Use minimap2 with -Y to use soft clipping for suplimentary alignments.";
+    case kErrCigarOp: return "Unhandled CIGAR OPT";
+    case kErrCigarLen: return "Assertion failed: read_pos < seq_len (CIGAR consumes more bases than the read has)";
+    case kErrRefRange: return "Assertion failed: ref_pos >= 0 && ref_pos < ref_len (alignment runs past the contig)";
+    case kErrNoContig: return "Contig not found in reference provided";
+    case kErrMMBase: return "Invalid base in MM tag";
+    case kErrMMStrand: return "Invalid strand in MM tag";
+    case kErrMMCode: return "Invalid base modification code in MM tag. Modification codes should be either numeric or alphabetic, not both, and cannot be empty.";
+    case kErrMMSkip: return "Invalid skip count in MM tag";
+    case kErrMMRank: return "Read pos cannot exceed seq len (MM tag skips more canonical bases than the read has)";
+    case kErrMLIndex: return "mod prob index mismatch. ml_idx >= ml_len";
+    case kErrTooManyCodes: return "too many modification codes (library limit: 8 per MM block, 8 characters per code, 256 distinct codes)";
+    case kErrSeqTooLong: return "read longer than 2^28 bases (library limit)";
+    default: return "unknown per-read error";
+    }
+}
+
+int setup_slot(mmc_ctx *ctx, Slot &s) {
+    const mmc_opts_t &o = ctx->opts;
+    const size_t R = o.max_reads;
+    // pool capacities (bytes).  Any pool filling up ends the batch early, which never changes results.
+    size_t cap_seq = align_up(o.max_bytes / 2 + 4096, 64), cap_cig = align_up(o.max_bytes / 2 + 4096, 64);
+    size_t cap_mm = align_up(o.max_bytes / 2 + 4096, 64), cap_ml = align_up(o.max_bytes / 4 + 4096, 64);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
+    s.o_tid = take(R * 4); s.o_pos = take(R * 4); s.o_lseq = take(R * 4); s.o_ncig = take(R * 4);
+    s.o_mmlen = take(R * 4); s.o_mllen = take(R * 4);
+    s.o_cigoff = take(R * 8); s.o_seqoff = take(R * 8); s.o_mmoff = take(R * 8); s.o_mloff = take(R * 8);
+    s.o_flag = take(R * 2); s.o_hp = take(R);
+    s.o_cigar = take(cap_cig + kSlack); s.o_seq = take(cap_seq + kSlack);
+    s.o_mm = take(cap_mm + kSlack); s.o_ml = take(cap_ml + kSlack);
+    s.arena_bytes = off;
+    CU(ctx, cudaMallocHost((void **)&s.h_arena, s.arena_bytes));
+    CU(ctx, cudaMalloc((void **)&s.d_arena, s.arena_bytes));
+    CU(ctx, cudaMemset(s.d_arena, 0, s.arena_bytes));
+    CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreate(&s.ev_h0)); CU(ctx, cudaEventCreate(&s.ev_h1));
+    CU(ctx, cudaEventCreate(&s.ev_k0)); CU(ctx, cudaEventCreate(&s.ev_k1));
+    CU(ctx, cudaMalloc((void **)&s.d_state, 64));
+    CU(ctx, cudaMallocHost((void **)&s.h_state, 64));
+    if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
+    mmc_batch_t &b = s.pub;
+    memset(&b, 0, sizeof(b));
+    b.max_reads = (uint32_t)R;
+    uint8_t *h = s.h_arena;
+    b.tid = (int32_t *)(h + s.o_tid); b.pos = (int32_t *)(h + s.o_pos);
+    b.l_seq = (uint32_t *)(h + s.o_lseq); b.n_cigar = (uint32_t *)(h + s.o_ncig);
+    b.mm_len = (uint32_t *)(h + s.o_mmlen); b.ml_len = (uint32_t *)(h + s.o_mllen);
+    b.cigar_off = (uint64_t *)(h + s.o_cigoff); b.seq_off = (uint64_t *)(h + s.o_seqoff);
+    b.mm_off = (uint64_t *)(h + s.o_mmoff); b.ml_off = (uint64_t *)(h + s.o_mloff);
+    b.flag = (uint16_t *)(h + s.o_flag); b.hp = h + s.o_hp;
+    b.cigar = (uint32_t *)(h + s.o_cigar); b.cigar_cap = cap_cig / 4;
+    b.seq4 = h + s.o_seq; b.seq_cap = cap_seq;
+    b.mm = (char *)(h + s.o_mm); b.mm_cap = cap_mm;
+    b.ml = h + s.o_ml; b.ml_cap = cap_ml;
+    b.priv = &s;
+    return MMC_OK;
+}
+
+Slot *slot_of(mmc_ctx *ctx, mmc_batch_t *b) {
+    if (!b) return nullptr;
+    for (Slot &s : ctx->slots) if (&s.pub == b) return &s;
+    return nullptr;
+}
+
+int upload(mmc_ctx *ctx, Slot &s) {
+    const mmc_batch_t &b = s.pub;
+    const size_t n = b.n_reads;
+    if (n > b.max_reads || b.cigar_used > b.cigar_cap || b.seq_used > b.seq_cap || b.mm_used > b.mm_cap || b.ml_used > b.ml_cap)
+        return fail(ctx, MMC_EINVAL, "batch exceeds its capacities");
+    uint64_t bytes = 0;
+    CU(ctx, cudaEventRecord(s.ev_h0, s.stream));
+    auto cp = [&](size_t off, size_t len) -> cudaError_t {
+        if (!len) return cudaSuccess;
+        bytes += len;
+        return cudaMemcpyAsync(s.d_arena + off, s.h_arena + off, len, cudaMemcpyHostToDevice, s.stream);
+    };
+    CU(ctx, cp(s.o_tid, n * 4)); CU(ctx, cp(s.o_pos, n * 4)); CU(ctx, cp(s.o_lseq, n * 4)); CU(ctx, cp(s.o_ncig, n * 4));
+    CU(ctx, cp(s.o_mmlen, n * 4)); CU(ctx, cp(s.o_mllen, n * 4));
+    CU(ctx, cp(s.o_cigoff, n * 8)); CU(ctx, cp(s.o_seqoff, n * 8)); CU(ctx, cp(s.o_mmoff, n * 8)); CU(ctx, cp(s.o_mloff, n * 8));
+    CU(ctx, cp(s.o_flag, n * 2)); CU(ctx, cp(s.o_hp, n));
+    CU(ctx, cp(s.o_cigar, b.cigar_used * 4)); CU(ctx, cp(s.o_seq, b.seq_used));
+    CU(ctx, cp(s.o_mm, b.mm_used)); CU(ctx, cp(s.o_ml, b.ml_used));
+    CU(ctx, cudaEventRecord(s.ev_h1, s.stream));
+    ctx->tm.h2d_bytes += bytes;
+    s.uploaded = true; s.h2d_pending = true;
+    s.n_reads_submitted = (uint32_t)n;
+    return MMC_OK;
+}
+
+int launch_decode(mmc_ctx *ctx, Slot &s) {
+    const mmc_batch_t &b = s.pub;
+    const uint32_t n = s.n_reads_submitted;
+    // reset the slot's device state: err = ~0, view_n = 0, work counter = 0
+    s.h_state[0] = ~0ull; s.h_state[1] = 0; s.h_state[2] = 0;
+    CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 24, cudaMemcpyHostToDevice, s.stream));
+    if (n == 0) { s.in_flight = true; s.timed = false; return MMC_OK; }
+
+    uint32_t max_cig = 0, max_l = 0;
+    for (uint32_t i = 0; i < n; ++i) { max_cig = std::max(max_cig, b.n_cigar[i]); max_l = std::max(max_l, b.l_seq[i]); }
+    unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
+    if (grid == 0) grid = 1;
+    uint32_t cig_words = max_cig > (uint32_t)ctx->cig_smem_cap ? (uint32_t)align_up(max_cig, 32) : 0;
+    uint32_t bm_words = ((max_l + 31u) >> 5) > (uint32_t)ctx->bitmap_smem_words ? (uint32_t)align_up((max_l + 31u) >> 5, 32) : 0;
+    size_t per_cta = 2 * (size_t)cig_words + bm_words;
+    if (per_cta) {
+        size_t need = per_cta * grid;
+        if (need > s.scratch_words) {
+            CU(ctx, cudaStreamSynchronize(s.stream));
+            if (s.d_scratch) CU(ctx, cudaFree(s.d_scratch));
+            s.d_scratch = nullptr; s.scratch_words = 0;
+            CU(ctx, cudaMalloc((void **)&s.d_scratch, need * 4));
+            s.scratch_words = need;
+        }
+    }
+
+    DecodeParams P;
+    memset(&P, 0, sizeof(P));
+    uint8_t *d = s.d_arena;
+    P.n_reads = n;
+    P.tid = (const int32_t *)(d + s.o_tid); P.pos = (const int32_t *)(d + s.o_pos);
+    P.l_seq = (const uint32_t *)(d + s.o_lseq); P.n_cigar = (const uint32_t *)(d + s.o_ncig);
+    P.mm_len = (const uint32_t *)(d + s.o_mmlen); P.ml_len = (const uint32_t *)(d + s.o_mllen);
+    P.cigar_off = (const unsigned long long *)(d + s.o_cigoff); P.seq_off = (const unsigned long long *)(d + s.o_seqoff);
+    P.mm_off = (const unsigned long long *)(d + s.o_mmoff); P.ml_off = (const unsigned long long *)(d + s.o_mloff);
+    P.flag = (const uint16_t *)(d + s.o_flag); P.hp = d + s.o_hp;
+    P.cigar = (const uint32_t *)(d + s.o_cigar); P.seq4 = d + s.o_seq; P.mm = d + s.o_mm; P.ml = d + s.o_ml;
+    P.req = ctx->d_req; P.n_req = ctx->opts.n_mods; P.wild_req = ctx->wild_req;
+    P.insertions = ctx->opts.insertions; P.haplotypes = ctx->opts.haplotypes; P.subtool = ctx->opts.subtool;
+    P.code_keys = ctx->d_code_keys;
+    P.n_contigs = (int32_t)ctx->contigs.size(); P.contigs = ctx->d_contigs;
+    P.n_code_slots = ctx->n_code_slots; P.n_hap_slots = ctx->n_hap_slots;
+    P.touch_lo = ctx->d_touch; P.touch_hi = ctx->d_touch + ctx->contigs.size();
+    P.sparse = ctx->d_sparse; P.sparse_cap = ctx->sparse_cap; P.sparse_n = ctx->d_sparse_n;
+    P.view = s.d_view; P.view_cap = ctx->view_cap; P.view_n = s.d_state + 1;
+    P.err = s.d_state;
+    P.scratch = per_cta ? s.d_scratch : nullptr;
+    P.scratch_words_per_cta = per_cta; P.scratch_cig_words = cig_words;
+    P.work_counter = (uint32_t *)(s.d_state + 2);
+    P.cig_smem_cap = ctx->cig_smem_cap; P.bitmap_smem_words = ctx->bitmap_smem_words; P.idx_smem_cap = ctx->idx_smem_cap;
+
+    CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    MMC_LAUNCH(k_decode, grid, (unsigned)ctx->threads, s.stream, P);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(s.ev_k1, s.stream));
+    CU(ctx, cudaMemcpyAsync(s.h_state, s.d_state, 16, cudaMemcpyDeviceToHost, s.stream));
+    ctx->tm.kernel_launches += 1;
+    ctx->tm.batches += 1;
+    ctx->tm.reads += n;
+    s.in_flight = true; s.timed = true;
+    return MMC_OK;
+}
+
+int wait_slot(mmc_ctx *ctx, Slot &s) {
+    if (!s.in_flight) return MMC_OK;
+    CU(ctx, cudaStreamSynchronize(s.stream));
+    s.in_flight = false;
+    if (s.h2d_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.ev_h0, s.ev_h1) == cudaSuccess) ctx->tm.h2d_ms += ms;
+        s.h2d_pending = false;
+    }
+    if (s.timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) ctx->tm.decode_ms += ms;
+    }
+    if (s.n_reads_submitted && s.h_state[0] != ~0ull) {
+        uint32_t read = (uint32_t)(s.h_state[0] >> 32), code = (uint32_t)(s.h_state[0] & 0xffffffffu);
+        fail(ctx, MMC_EREAD, "read #%u of the batch: %s", read, read_error_text(code));
+        ctx->err += "\x1f" + std::to_string(read);           // machine-readable suffix: \x1f<read index>
+        return MMC_EREAD;
+    }
+    if (ctx->opts.subtool == MMC_VIEW && s.h_state[1] > ctx->view_cap)
+        return fail(ctx, MMC_ENOMEM, "view record buffer overflow (%llu > %llu); raise view_capacity",
+                    (unsigned long long)s.h_state[1], (unsigned long long)ctx->view_cap);
+    return MMC_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int mmc_abi_version(void) { return MMC_ABI_VERSION; }
+
+const char *mmc_strerror(const mmc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const char *const *names, const uint32_t *lens) {
+    if (!out || !opts || opts->struct_size != sizeof(mmc_opts_t)) return fail(nullptr, MMC_EINVAL, "mmc_create: bad opts (ABI mismatch?)");
+    if (opts->subtool != MMC_FREQ && opts->subtool != MMC_VIEW) return fail(nullptr, MMC_EINVAL, "mmc_create: subtool must be MMC_FREQ or MMC_VIEW");
+    if (opts->n_mods < 1 || opts->n_mods > MMC_MAX_MODS || !opts->mods) return fail(nullptr, MMC_EINVAL, "mmc_create: need 1..%d modification codes", MMC_MAX_MODS);
+    if (n_contigs < 0 || (n_contigs > 0 && (!names || !lens))) return fail(nullptr, MMC_EINVAL, "mmc_create: bad contig table");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(nullptr, MMC_ECUDA, "mmc_create: no CUDA device available (libminimod_cuda has no CPU fallback)");
+    if (opts->device < 0 || opts->device >= ndev) return fail(nullptr, MMC_EINVAL, "mmc_create: device %d out of range (0..%d)", opts->device, ndev - 1);
+
+    mmc_ctx *ctx = new mmc_ctx();
+    ctx->opts = *opts;
+    mmc_opts_t &o = ctx->opts;
+    if (o.n_slots <= 0) o.n_slots = 3;
+    if (o.max_reads == 0) o.max_reads = 512;                 // init_opt(), src/minimod.c:487
+    if (o.max_bytes == 0) o.max_bytes = 20 * 1000 * 1000;    // src/minimod.c:488
+    if (o.dense_haps <= 0) o.dense_haps = 4;
+    if (o.dense_codes <= 0) o.dense_codes = 8;
+    if (o.dense_haps > 255) o.dense_haps = 255;
+    ctx->mods.assign(opts->mods, opts->mods + opts->n_mods);
+    o.mods = ctx->mods.data();
+    if (const char *e = getenv("MMC_DECODE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kMaxThreads && v % 32 == 0) ctx->threads = v; }
+    if (const char *e = getenv("MMC_TEST_SMALL_SMEM")) {     // test hook: force the global-scratch paths
+        if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
+    }
+
+#define CUC(call)                                                                                            \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            fail(nullptr, MMC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            mmc_destroy(ctx);                                                                                \
+            return MMC_ECUDA;                                                                                \
+        }                                                                                                    \
+    } while (0)
+
+    CUC(cudaSetDevice(o.device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, o.device));
+    ctx->sm_count = prop.multiProcessorCount;
+    int occ = 1;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, ctx->threads, 0));
+    ctx->ctas_per_sm = occ < 1 ? 1 : occ;
+
+    // ---- -c entries -> device tables
+    std::vector<ReqMod> req(o.n_mods);
+    ctx->wild_req = -1;
+    for (int i = 0; i < o.n_mods; ++i) {
+        const mmc_mod_t &m = ctx->mods[i];
+        ReqMod &r = req[i];
+        memset(&r, 0, sizeof(r));
+        size_t cl = strnlen(m.code, MMC_MAX_CODE_LEN + 1), xl = strnlen(m.context, MMC_MAX_CONTEXT + 1);
+        if (cl == 0 || cl > MMC_MAX_CODE_LEN || xl == 0 || xl > MMC_MAX_CONTEXT) {
+            fail(nullptr, MMC_EINVAL, "mmc_create: modification code/context %d empty or too long", i);
+            mmc_destroy(ctx); return MMC_EINVAL;
+        }
+        r.key = pack_code(m.code);
+        if (!strcmp(m.code, "*")) ctx->wild_req = i;
+        if (!strcmp(m.context, "*")) r.ctx_len = 0;
+        else {
+            r.ctx_len = (int32_t)xl;
+            for (size_t k = 0; k < xl; ++k) {
+                char c = m.context[k];
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') {
+                    fail(nullptr, MMC_EINVAL, "mmc_create: context '%s' must be upper-case A/C/G/T/N or '*'", m.context);
+                    mmc_destroy(ctx); return MMC_EINVAL;
+                }
+                r.pat[k] = (uint8_t)c;
+                char b = m.context[xl - 1 - k];                 // reverse complement, src/ref.c:183-194
+                r.pat_rc[k] = (uint8_t)(b == 'A' ? 'T' : b == 'C' ? 'G' : b == 'G' ? 'C' : b == 'T' ? 'A' : 'N');
+            }
+        }
+        memcpy(r.lut, m.call_lut, 256);
+    }
+    CUC(cudaMalloc((void **)&ctx->d_req, sizeof(ReqMod) * req.size()));
+    CUC(cudaMemcpy(ctx->d_req, req.data(), sizeof(ReqMod) * req.size(), cudaMemcpyHostToDevice));
+    std::vector<unsigned long long> keys(kCodeTable, 0ull);
+    if (ctx->wild_req < 0) for (int i = 0; i < o.n_mods; ++i) keys[i] = req[i].key;
+    CUC(cudaMalloc((void **)&ctx->d_code_keys, sizeof(unsigned long long) * kCodeTable));
+    CUC(cudaMemcpy(ctx->d_code_keys, keys.data(), sizeof(unsigned long long) * kCodeTable, cudaMemcpyHostToDevice));
+
+    ctx->n_code_slots = ctx->wild_req >= 0 ? o.dense_codes : o.n_mods;
+    ctx->n_hap_slots = o.haplotypes ? 1 + o.dense_haps : 1;
+
+    // ---- contigs
+    ctx->contigs.resize(n_contigs);
+    for (int i = 0; i < n_contigs; ++i) { ctx->contigs[i].name = names[i] ? names[i] : ""; ctx->contigs[i].len = lens[i]; }
+    size_t nc = std::max<size_t>(1, (size_t)n_contigs);
+    CUC(cudaMalloc((void **)&ctx->d_contigs, sizeof(ContigDev) * nc));
+    CUC(cudaMemset(ctx->d_contigs, 0, sizeof(ContigDev) * nc));
+    CUC(cudaMalloc((void **)&ctx->d_touch, sizeof(int32_t) * 2 * nc));
+
+    // ---- side buffers
+    ctx->sparse_cap = o.sparse_capacity ? o.sparse_capacity : (o.subtool == MMC_FREQ ? std::max<uint64_t>(1u << 20, o.max_bytes / 8) : 16);
+    CUC(cudaMalloc((void **)&ctx->d_sparse, sizeof(SparseRec) * ctx->sparse_cap));
+    CUC(cudaMalloc((void **)&ctx->d_sparse_n, 8));
+    CUC(cudaMemset(ctx->d_sparse_n, 0, 8));
+    ctx->view_cap = o.view_capacity ? o.view_capacity : std::max<uint64_t>(1u << 16, o.max_bytes);
+    CUC(cudaStreamCreateWithFlags(&ctx->fin_stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&ctx->ev_f0)); CUC(cudaEventCreate(&ctx->ev_f1));
+
+    ctx->slots.resize(o.n_slots);
+    for (Slot &s : ctx->slots) {
+        int rc = setup_slot(ctx, s);
+        if (rc != MMC_OK) { g_create_error = ctx->err; mmc_destroy(ctx); return rc; }
+    }
+    // touch ranges start empty: [lo x n_contigs][hi x n_contigs]
+    {
+        const size_t m = (size_t)n_contigs;
+        std::vector<int32_t> t2(2 * std::max<size_t>(1, m));
+        for (size_t i = 0; i < m; ++i) { t2[i] = INT32_MAX; t2[m + i] = 0; }
+        if (m) CUC(cudaMemcpy(ctx->d_touch, t2.data(), sizeof(int32_t) * 2 * m, cudaMemcpyHostToDevice));
+    }
+#undef CUC
+    *out = ctx;
+    return MMC_OK;
+}
+
+void mmc_destroy(mmc_ctx *ctx) {
+    if (!ctx) return;
+    cudaDeviceSynchronize();
+    for (Slot &s : ctx->slots) {
+        if (s.h_arena) cudaFreeHost(s.h_arena);
+        if (s.d_arena) cudaFree(s.d_arena);
+        if (s.d_state) cudaFree(s.d_state);
+        if (s.h_state) cudaFreeHost(s.h_state);
+        if (s.d_view) cudaFree(s.d_view);
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        if (s.ev_h0) cudaEventDestroy(s.ev_h0);
+        if (s.ev_h1) cudaEventDestroy(s.ev_h1);
+        if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (ContigHost &c : ctx->contigs) {
+        if (c.dev.ref2) cudaFree((void *)c.dev.ref2);
+        if (c.dev.excm) cudaFree((void *)c.dev.excm);
+        if (c.dev.cells) cudaFree(c.dev.cells);
+        if (c.d_exc_start) cudaFree(c.d_exc_start);
+        if (c.d_exc_letter) cudaFree(c.d_exc_letter);
+    }
+    if (ctx->d_req) cudaFree(ctx->d_req);
+    if (ctx->d_code_keys) cudaFree(ctx->d_code_keys);
+    if (ctx->d_contigs) cudaFree(ctx->d_contigs);
+    if (ctx->d_touch) cudaFree(ctx->d_touch);
+    if (ctx->d_sparse) cudaFree(ctx->d_sparse);
+    if (ctx->d_sparse_n) cudaFree(ctx->d_sparse_n);
+    if (ctx->d_ascii) cudaFree(ctx->d_ascii);
+    if (ctx->d_exc_tmp_start) cudaFree(ctx->d_exc_tmp_start);
+    if (ctx->d_exc_tmp_letter) cudaFree(ctx->d_exc_tmp_letter);
+    if (ctx->d_exc_n) cudaFree(ctx->d_exc_n);
+    if (ctx->ev_f0) cudaEventDestroy(ctx->ev_f0);
+    if (ctx->ev_f1) cudaEventDestroy(ctx->ev_f1);
+    if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
+    delete ctx;
+}
+
+int mmc_ref_add(mmc_ctx *ctx, int32_t tid, const char *seq, uint32_t len) {
+    if (!ctx) return MMC_EINVAL;
+    if (tid < 0 || (size_t)tid >= ctx->contigs.size()) return fail(ctx, MMC_EINVAL, "mmc_ref_add: tid %d out of range", tid);
+    ContigHost &c = ctx->contigs[tid];
+    if (c.loaded) return fail(ctx, MMC_ESTATE, "mmc_ref_add: contig %s added twice", c.name.c_str());
+    if (len != c.len)                                        // the reference asserts this per read, src/mod.c:861
+        return fail(ctx, MMC_EINVAL, "ref_len:%u target_len:%u (contig %s: reference and BAM header lengths differ)", len, c.len, c.name.c_str());
+    if (!seq && len) return fail(ctx, MMC_EINVAL, "mmc_ref_add: null sequence");
+    const size_t spp = 2 * (size_t)ctx->n_code_slots * ctx->n_hap_slots;
+    const size_t n32 = ((size_t)len + 31) / 32;
+    size_t free_b = 0, total_b = 0;
+    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t need = (ctx->opts.subtool == MMC_FREQ ? (size_t)len * spp * 8 : 0) + n32 * 12 + (64u << 20);
+    if (need > free_b)
+        return fail(ctx, MMC_ENOMEM, "contig %s needs %.1f GB of HBM for its packed reference and dense count array (%zu cells per position) but %.1f GB are free; shard contigs across GPUs or lower dense_haps/dense_codes",
+                    c.name.c_str(), need / 1e9, spp, free_b / 1e9);
+    uint32_t *ref2 = nullptr, *excm = nullptr;
+    CU(ctx, cudaMalloc((void **)&ref2, std::max<size_t>(8, n32 * 8)));
+    CU(ctx, cudaMalloc((void **)&excm, std::max<size_t>(4, n32 * 4)));
+    c.dev.ref2 = ref2; c.dev.excm = excm; c.dev.len = len;
+    if (ctx->opts.subtool == MMC_FREQ) {
+        CU(ctx, cudaMalloc((void **)&c.dev.cells, std::max<size_t>(8, (size_t)len * spp * 8)));
+        CU(ctx, cudaMemsetAsync(c.dev.cells, 0, std::max<size_t>(8, (size_t)len * spp * 8), ctx->fin_stream));
+    }
+    if (!ctx->d_ascii) {
+        ctx->ascii_cap = 64u << 20;
+        CU(ctx, cudaMalloc((void **)&ctx->d_ascii, ctx->ascii_cap));
+        CU(ctx, cudaMalloc((void **)&ctx->d_exc_tmp_start, sizeof(uint32_t) * kExcCap));
+        CU(ctx, cudaMalloc((void **)&ctx->d_exc_tmp_letter, kExcCap));
+        CU(ctx, cudaMalloc((void **)&ctx->d_exc_n, 4));
+    }
+    CU(ctx, cudaMemsetAsync(ctx->d_exc_n, 0, 4, ctx->fin_stream));
+    uint32_t prev = 0;
+    for (size_t off = 0; off < len; off += ctx->ascii_cap) {
+        size_t n = std::min<size_t>(ctx->ascii_cap, len - off);
+        CU(ctx, cudaMemcpyAsync(ctx->d_ascii, seq + off, n, cudaMemcpyHostToDevice, ctx->fin_stream));
+        RefPackParams rp;
+        rp.ascii = ctx->d_ascii; rp.g_first = (uint32_t)off; rp.n = (uint32_t)n; rp.prev_letter = prev;
+        rp.ref2 = ref2; rp.excm = excm;
+        rp.exc_start = ctx->d_exc_tmp_start; rp.exc_letter = ctx->d_exc_tmp_letter; rp.exc_cap = kExcCap; rp.exc_n = ctx->d_exc_n;
+        unsigned threads = 256, grid = (unsigned)((n + 32 * (size_t)threads - 1) / (32 * (size_t)threads));
+        MMC_LAUNCH(k_ref_pack, grid, threads, ctx->fin_stream, rp);
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 1;
+        CU(ctx, cudaStreamSynchronize(ctx->fin_stream));    // seq+off may be pageable; keep it simple and ordered
+        unsigned char last = (unsigned char)seq[off + n - 1];
+        if (last >= 'a' && last <= 'z') last -= 32;
+        prev = last == 'U' ? 'T' : last;
+    }
+    uint32_t n_exc = 0;
+    CU(ctx, cudaMemcpy(&n_exc, ctx->d_exc_n, 4, cudaMemcpyDeviceToHost));
+    if (n_exc > kExcCap)
+        return fail(ctx, MMC_ENOMEM, "contig %s has more than %u runs of non-ACGT letters (library limit)", c.name.c_str(), kExcCap);
+    if (n_exc) {
+        std::vector<uint32_t> st(n_exc);
+        std::vector<uint8_t> le(n_exc);
+        CU(ctx, cudaMemcpy(st.data(), ctx->d_exc_tmp_start, 4 * (size_t)n_exc, cudaMemcpyDeviceToHost));
+        CU(ctx, cudaMemcpy(le.data(), ctx->d_exc_tmp_letter, n_exc, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> order(n_exc);
+        for (uint32_t i = 0; i < n_exc; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return st[a] < st[b]; });
+        std::vector<uint32_t> st2(n_exc);
+        std::vector<uint8_t> le2(n_exc);
+        for (uint32_t i = 0; i < n_exc; ++i) { st2[i] = st[order[i]]; le2[i] = le[order[i]]; }
+        CU(ctx, cudaMalloc((void **)&c.d_exc_start, 4 * (size_t)n_exc));
+        CU(ctx, cudaMalloc((void **)&c.d_exc_letter, n_exc));
+        CU(ctx, cudaMemcpy(c.d_exc_start, st2.data(), 4 * (size_t)n_exc, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(c.d_exc_letter, le2.data(), n_exc, cudaMemcpyHostToDevice));
+    }
+    c.dev.exc_start = c.d_exc_start; c.dev.exc_letter = c.d_exc_letter; c.dev.n_exc = n_exc;
+    c.loaded = true;
+    ctx->committed = false;
+    return MMC_OK;
+}
+
+int mmc_ref_commit(mmc_ctx *ctx) {
+    if (!ctx) return MMC_EINVAL;
+    std::vector<ContigDev> tab(ctx->contigs.size());
+    for (size_t i = 0; i < tab.size(); ++i) {
+        if (ctx->contigs[i].loaded) tab[i] = ctx->contigs[i].dev; else memset(&tab[i], 0, sizeof(ContigDev));
+    }
+    if (!tab.empty()) CU(ctx, cudaMemcpy(ctx->d_contigs, tab.data(), sizeof(ContigDev) * tab.size(), cudaMemcpyHostToDevice));
+    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    ctx->committed = true;
+    return MMC_OK;
+}
+
+int mmc_batch_acquire(mmc_ctx *ctx, mmc_batch_t **batch) {
+    if (!ctx || !batch) return MMC_EINVAL;
+    Slot *pick = nullptr;
+    for (Slot &s : ctx->slots) if (!s.acquired) { pick = &s; break; }
+    if (!pick) return fail(ctx, MMC_ESTATE, "mmc_batch_acquire: all %d slots are in use; release one first", (int)ctx->slots.size());
+    int rc = wait_slot(ctx, *pick);
+    if (rc != MMC_OK) return rc;
+    pick->acquired = true; pick->uploaded = false;
+    mmc_batch_t &b = pick->pub;
+    b.n_reads = 0; b.cigar_used = b.seq_used = b.mm_used = b.ml_used = 0;
+    *batch = &b;
+    return MMC_OK;
+}
+
+int mmc_batch_upload(mmc_ctx *ctx, mmc_batch_t *batch) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s || !s->acquired) return fail(ctx, MMC_ESTATE, "mmc_batch_upload: not an acquired batch");
+    if (!ctx->committed) return fail(ctx, MMC_ESTATE, "mmc_batch_upload: call mmc_ref_commit() first");
+    int rc = wait_slot(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    rc = upload(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    CU(ctx, cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev_h0, s->ev_h1) == cudaSuccess) ctx->tm.h2d_ms += ms;
+    s->h2d_pending = false;
+    return MMC_OK;
+}
+
+int mmc_batch_launch(mmc_ctx *ctx, mmc_batch_t *batch) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s || !s->acquired || !s->uploaded) return fail(ctx, MMC_ESTATE, "mmc_batch_launch: batch was not uploaded");
+    int rc = wait_slot(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    return launch_decode(ctx, *s);
+}
+
+int mmc_batch_submit(mmc_ctx *ctx, mmc_batch_t *batch) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s || !s->acquired) return fail(ctx, MMC_ESTATE, "mmc_batch_submit: not an acquired batch");
+    if (!ctx->committed) return fail(ctx, MMC_ESTATE, "mmc_batch_submit: call mmc_ref_commit() first");
+    int rc = wait_slot(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    rc = upload(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    return launch_decode(ctx, *s);
+}
+
+int mmc_batch_wait(mmc_ctx *ctx, mmc_batch_t *batch) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s) return fail(ctx, MMC_ESTATE, "mmc_batch_wait: unknown batch");
+    return wait_slot(ctx, *s);
+}
+
+int mmc_batch_release(mmc_ctx *ctx, mmc_batch_t *batch) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s) return fail(ctx, MMC_ESTATE, "mmc_batch_release: unknown batch");
+    int rc = wait_slot(ctx, *s);
+    s->acquired = false; s->uploaded = false;
+    return rc;
+}
+
+int mmc_sync(mmc_ctx *ctx) {
+    if (!ctx) return MMC_EINVAL;
+    int first = MMC_OK;
+    for (Slot &s : ctx->slots) { int rc = wait_slot(ctx, s); if (rc != MMC_OK && first == MMC_OK) first = rc; }
+    return first;
+}
+
+int mmc_last_decode_ms(mmc_ctx *ctx, mmc_batch_t *batch, double *ms) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s || !ms) return MMC_EINVAL;
+    int rc = wait_slot(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    float f = 0;
+    CU(ctx, cudaEventElapsedTime(&f, s->ev_k0, s->ev_k1));
+    *ms = f;
+    return MMC_OK;
+}
+
+const char *mmc_code_name(const mmc_ctx *ctx, int32_t code) {
+    if (!ctx || code < 0) return "";
+    if (ctx->wild_req < 0) return code < ctx->opts.n_mods ? ctx->mods[code].code : "";
+    return (size_t)code < ctx->code_names.size() ? ctx->code_names[code].c_str() : "";
+}
+
+static int refresh_code_names(mmc_ctx *ctx) {
+    if (ctx->wild_req < 0) return MMC_OK;
+    std::vector<unsigned long long> keys(kCodeTable);
+    CU(ctx, cudaMemcpy(keys.data(), ctx->d_code_keys, sizeof(unsigned long long) * kCodeTable, cudaMemcpyDeviceToHost));
+    ctx->code_names.assign(kCodeTable, std::string());
+    for (int i = 0; i < kCodeTable; ++i) ctx->code_names[i] = unpack_code(keys[i]);
+    return MMC_OK;
+}
+
+int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
+    if (!ctx || !recs || !n_recs) return MMC_EINVAL;
+    if (ctx->opts.subtool != MMC_FREQ) return fail(ctx, MMC_ESTATE, "mmc_freq_finalize: context was created for view");
+    int rc = mmc_sync(ctx);
+    if (rc != MMC_OK) return rc;
+    rc = refresh_code_names(ctx);
+    if (rc != MMC_OK) return rc;
+    const size_t nc = ctx->contigs.size();
+    std::vector<int32_t> touch(2 * std::max<size_t>(1, nc));
+    if (nc) CU(ctx, cudaMemcpy(touch.data(), ctx->d_touch, sizeof(int32_t) * 2 * nc, cudaMemcpyDeviceToHost));
+    const uint32_t spp = 2u * (uint32_t)ctx->n_code_slots * (uint32_t)ctx->n_hap_slots;
+
+    struct Job { int32_t tid; int32_t lo; uint64_t n_cells; uint64_t n_tiles; uint64_t tile0; };
+    std::vector<Job> jobs;
+    uint64_t tiles = 0;
+    for (size_t i = 0; i < nc; ++i) {
+        if (!ctx->contigs[i].loaded) continue;
+        int32_t lo = touch[i], hi = touch[nc + i];
+        if (lo >= hi) continue;
+        Job j; j.tid = (int32_t)i; j.lo = lo; j.n_cells = (uint64_t)(hi - lo) * spp;
+        j.n_tiles = (j.n_cells + kTileCells - 1) / kTileCells; j.tile0 = tiles;
+        tiles += j.n_tiles;
+        jobs.push_back(j);
+    }
+    std::vector<mmc_freq_rec_t> dense;
+    uint32_t *d_tile_count = nullptr; unsigned long long *d_tile_off = nullptr, *d_totals = nullptr;
+    FreqRecDev *d_out = nullptr;
+    CU(ctx, cudaEventRecord(ctx->ev_f0, ctx->fin_stream));
+    if (tiles) {
+        CU(ctx, cudaMalloc((void **)&d_tile_count, 4 * tiles));
+        CU(ctx, cudaMalloc((void **)&d_tile_off, 8 * tiles));
+        CU(ctx, cudaMalloc((void **)&d_totals, 8 * jobs.size()));
+        std::vector<FinalizeParams> fps(jobs.size());
+        for (size_t k = 0; k < jobs.size(); ++k) {
+            const Job &j = jobs[k];
+            FinalizeParams &fp = fps[k];
+            memset(&fp, 0, sizeof(fp));
+            fp.cells = ctx->contigs[j.tid].dev.cells + (uint64_t)j.lo * spp;
+            fp.n_cells = j.n_cells; fp.tid = j.tid; fp.lo = j.lo;
+            fp.n_code_slots = ctx->n_code_slots; fp.n_hap_slots = ctx->n_hap_slots; fp.haplotypes = ctx->opts.haplotypes;
+            fp.tile_count = d_tile_count + j.tile0; fp.tile_offset = d_tile_off + j.tile0; fp.cells_per_tile = kTileCells;
+            MMC_LAUNCH(k_count_nonzero, (unsigned)j.n_tiles, 256u, ctx->fin_stream, fp);
+            CU(ctx, cudaGetLastError());
+            MMC_LAUNCH(k_scan_tiles, 1u, 256u, ctx->fin_stream, fp.tile_count, fp.tile_offset, (uint32_t)j.n_tiles, d_totals + k);
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 2;
+        }
+        std::vector<unsigned long long> totals(jobs.size());
+        CU(ctx, cudaMemcpyAsync(totals.data(), d_totals, 8 * jobs.size(), cudaMemcpyDeviceToHost, ctx->fin_stream));
+        CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+        uint64_t total = 0;
+        for (unsigned long long t : totals) total += t;
+        if (total) {
+            CU(ctx, cudaMalloc((void **)&d_out, sizeof(FreqRecDev) * total));
+            uint64_t base = 0;
+            for (size_t k = 0; k < jobs.size(); ++k) {
+                if (!totals[k]) continue;
+                fps[k].out = d_out; fps[k].out_base = base;
+                MMC_LAUNCH(k_emit_records, (unsigned)jobs[k].n_tiles, 256u, ctx->fin_stream, fps[k]);
+                CU(ctx, cudaGetLastError());
+                ctx->tm.kernel_launches += 1;
+                base += totals[k];
+            }
+            dense.resize(total);
+            CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
+            CU(ctx, cudaMemcpyAsync(dense.data(), d_out, sizeof(FreqRecDev) * total, cudaMemcpyDeviceToHost, ctx->fin_stream));
+            ctx->tm.d2h_bytes += sizeof(FreqRecDev) * total;
+        } else {
+            CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
+        }
+    } else {
+        CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_f0, ctx->ev_f1) == cudaSuccess) ctx->tm.finalize_ms += ms;
+    }
+    if (d_tile_count) cudaFree(d_tile_count);
+    if (d_tile_off) cudaFree(d_tile_off);
+    if (d_totals) cudaFree(d_totals);
+    if (d_out) cudaFree(d_out);
+
+    // ---- sparse side buffer: sort + reduce on the host, then merge with the dense rows
+    unsigned long long sn = 0;
+    CU(ctx, cudaMemcpy(&sn, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost));
+    if (sn > ctx->sparse_cap)
+        return fail(ctx, MMC_ENOMEM, "sparse count buffer overflow (%llu records > capacity %llu); raise sparse_capacity",
+                    sn, (unsigned long long)ctx->sparse_cap);
+    std::vector<mmc_freq_rec_t> sparse;
+    if (sn) {
+        std::vector<SparseRec> raw(sn);
+        CU(ctx, cudaMemcpy(raw.data(), ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToHost));
+        ctx->tm.d2h_bytes += sizeof(SparseRec) * sn;
+        std::sort(raw.begin(), raw.end(), [](const SparseRec &x, const SparseRec &y) {
+            if (x.a != y.a) {
+                // order by tid, pos, strand, code == numeric order of a
+                return x.a < y.a;
+            }
+            uint32_t xi = x.b & 0xffffu, yi = y.b & 0xffffu;
+            if (xi != yi) return xi < yi;
+            // hap: '*' (256) first, then 0,1,...
+            int32_t xh = (int32_t)(x.b >> 16) == 256 ? -1 : (int32_t)(x.b >> 16), yh = (int32_t)(y.b >> 16) == 256 ? -1 : (int32_t)(y.b >> 16);
+            return xh < yh;
+        });
+        for (size_t i = 0; i < raw.size();) {
+            size_t j = i;
+            uint64_t called = 0, mod = 0;
+            while (j < raw.size() && raw[j].a == raw[i].a && raw[j].b == raw[i].b) { called += raw[j].w & 0xffffu; mod += raw[j].w >> 16; ++j; }
+            mmc_freq_rec_t r;
+            r.tid = (int32_t)(raw[i].a >> 41); r.pos = (int32_t)((raw[i].a >> 9) & 0xffffffffull);
+            r.strand = (uint8_t)((raw[i].a >> 8) & 1u); r.code = (uint8_t)(raw[i].a & 0xffu);
+            r.ins_offset = (uint16_t)(raw[i].b & 0xffffu);
+            uint32_t h9 = raw[i].b >> 16;
+            r.hap = h9 == 256 ? (int16_t)-1 : (int16_t)h9;
+            r.n_called = (uint32_t)called; r.n_mod = (uint32_t)mod; r.reserved = 0;
+            sparse.push_back(r);
+            i = j;
+        }
+    }
+    auto less = [](const mmc_freq_rec_t &x, const mmc_freq_rec_t &y) {
+        if (x.tid != y.tid) return x.tid < y.tid;
+        if (x.pos != y.pos) return x.pos < y.pos;
+        if (x.strand != y.strand) return x.strand < y.strand;
+        if (x.code != y.code) return x.code < y.code;
+        if (x.ins_offset != y.ins_offset) return x.ins_offset < y.ins_offset;
+        return x.hap < y.hap;
+    };
+    ctx->freq_out.clear();
+    ctx->freq_out.resize(dense.size() + sparse.size());
+    std::merge(dense.begin(), dense.end(), sparse.begin(), sparse.end(), ctx->freq_out.begin(), less);
+    *recs = ctx->freq_out.data();
+    *n_recs = ctx->freq_out.size();
+    return MMC_OK;
+}
+
+int mmc_freq_reset(mmc_ctx *ctx) {
+    if (!ctx) return MMC_EINVAL;
+    int rc = mmc_sync(ctx);
+    if (rc != MMC_OK) return rc;
+    const size_t nc = ctx->contigs.size();
+    std::vector<int32_t> touch(2 * std::max<size_t>(1, nc));
+    if (nc) CU(ctx, cudaMemcpy(touch.data(), ctx->d_touch, sizeof(int32_t) * 2 * nc, cudaMemcpyDeviceToHost));
+    const size_t spp = 2 * (size_t)ctx->n_code_slots * ctx->n_hap_slots;
+    for (size_t i = 0; i < nc; ++i) {
+        if (!ctx->contigs[i].loaded || !ctx->contigs[i].dev.cells) continue;
+        int32_t lo = touch[i], hi = touch[nc + i];
+        if (lo >= hi) continue;
+        CU(ctx, cudaMemsetAsync(ctx->contigs[i].dev.cells + (size_t)lo * spp, 0, (size_t)(hi - lo) * spp * 8, ctx->fin_stream));
+        touch[i] = INT32_MAX; touch[nc + i] = 0;
+    }
+    if (nc) CU(ctx, cudaMemcpyAsync(ctx->d_touch, touch.data(), sizeof(int32_t) * 2 * nc, cudaMemcpyHostToDevice, ctx->fin_stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_sparse_n, 0, 8, ctx->fin_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    return MMC_OK;
+}
+
+int mmc_view_fetch(mmc_ctx *ctx, mmc_batch_t *batch, const mmc_view_rec_t **recs, uint64_t *n_recs) {
+    Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
+    if (!s || !recs || !n_recs) return MMC_EINVAL;
+    if (ctx->opts.subtool != MMC_VIEW) return fail(ctx, MMC_ESTATE, "mmc_view_fetch: context was created for freq");
+    int rc = wait_slot(ctx, *s);
+    if (rc != MMC_OK) return rc;
+    rc = refresh_code_names(ctx);
+    if (rc != MMC_OK) return rc;
+    uint64_t n = s->n_reads_submitted ? s->h_state[1] : 0;
+    std::vector<ViewDev> raw(n);
+    if (n) {
+        CU(ctx, cudaMemcpy(raw.data(), s->d_view, sizeof(ViewDev) * n, cudaMemcpyDeviceToHost));
+        ctx->tm.d2h_bytes += sizeof(ViewDev) * n;
+    }
+    // first-wins de-duplication on (read, ref_pos, code string, uint16 ins_offset): add_view_entry(), src/mod.c:931-946
+    std::sort(raw.begin(), raw.end(), [](const ViewDev &x, const ViewDev &y) {
+        if (x.read != y.read) return x.read < y.read;
+        if (x.ref_pos != y.ref_pos) return x.ref_pos < y.ref_pos;
+        if (x.code != y.code) return x.code < y.code;
+        uint32_t xi = x.ins_off & 0xffffu, yi = y.ins_off & 0xffffu;
+        if (xi != yi) return xi < yi;
+        return x.order < y.order;
+    });
+    s->view_out.clear();
+    for (size_t i = 0; i < raw.size(); ++i) {
+        if (i && raw[i].read == raw[i - 1].read && raw[i].ref_pos == raw[i - 1].ref_pos && raw[i].code == raw[i - 1].code &&
+            (raw[i].ins_off & 0xffffu) == (raw[i - 1].ins_off & 0xffffu))
+            continue;
+        mmc_view_rec_t v;
+        v.read = raw[i].read; v.ref_pos = raw[i].ref_pos; v.read_pos = raw[i].read_pos; v.ins_offset = raw[i].ins_off;
+        v.code = raw[i].code; v.mod_prob = raw[i].prob;
+        v.strand = (uint8_t)((batch->flag[v.read] >> 4) & 1u); v.hp = batch->hp[v.read];
+        s->view_out.push_back(v);
+    }
+    *recs = s->view_out.data();
+    *n_recs = s->view_out.size();
+    return MMC_OK;
+}
+
+int mmc_dense_slice(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end, void **dev_ptr, uint64_t *n_cells) {
+    if (!ctx || !dev_ptr || !n_cells) return MMC_EINVAL;
+    if (tid < 0 || (size_t)tid >= ctx->contigs.size() || !ctx->contigs[tid].loaded || !ctx->contigs[tid].dev.cells)
+        return fail(ctx, MMC_EINVAL, "mmc_dense_slice: contig %d has no dense counts", tid);
+    if (start > end || end > ctx->contigs[tid].len) return fail(ctx, MMC_EINVAL, "mmc_dense_slice: bad range");
+    const size_t spp = 2 * (size_t)ctx->n_code_slots * ctx->n_hap_slots;
+    *dev_ptr = ctx->contigs[tid].dev.cells + (size_t)start * spp;
+    *n_cells = (uint64_t)(end - start) * spp;
+    return MMC_OK;
+}
+
+int mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out) {
+    if (!ctx || !out) return MMC_EINVAL;
+    *out = ctx->tm;
+    return MMC_OK;
+}
+
+int mmc_reset_timers(mmc_ctx *ctx) {
+    if (!ctx) return MMC_EINVAL;
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    return MMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// capi.cpp -- C entry points of libminimod_host.so: the host-side pieces (BAM reading,
+// load_db filtering/packing, FASTA, -c/-m parsing, text formatting) exposed so that the Python
+// mirror of the reference interface (minimod_b200/api.py) and the tests drive exactly the code
+// the `minimod` binary runs.  No compute happens here.
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "bam.h"
+#include "fasta.h"
+#include "format.h"
+#include "modopts.h"
+#include "pack.h"
+
+using namespace mmh;
+
+namespace {
+void set_err(char *err, int errlen, const std::string &msg) {
+    if (err && errlen > 0) { snprintf(err, (size_t)errlen, "%s", msg.c_str()); }
+}
+struct Loader { BatchLoader *bl; BatchMeta meta; };
+struct Fasta { std::vector<FastaRecord> recs; };
+}
+
+extern "C" {
+
+typedef struct {
+    int32_t total_reads; int32_t n_recs;
+    int64_t total_bytes; int64_t processed_bytes; int64_t ml_entries; int64_t bases;
+} mmh_stats_t;
+
+void *mmh_bam_open(const char *path, char *err, int errlen) {
+    BamFile *b = new BamFile();
+    std::string e;
+    if (!b->open(path, &e)) { set_err(err, errlen, e); delete b; return nullptr; }
+    return b;
+}
+void mmh_bam_close(void *h) { delete (BamFile *)h; }
+int mmh_bam_n_targets(void *h) { return (int)((BamFile *)h)->names.size(); }
+const char *mmh_bam_target_name(void *h, int i) { return ((BamFile *)h)->names[i].c_str(); }
+uint32_t mmh_bam_target_len(void *h, int i) { return ((BamFile *)h)->lens[i]; }
+
+void *mmh_loader_new(void *bam, int32_t batch_size, int64_t batch_bytes, int allow_secondary, int skip_supplementary, int keep_qnames) {
+    LoadOpts lo;
+    lo.batch_size = batch_size; lo.batch_size_bases = batch_bytes;
+    lo.allow_secondary = allow_secondary; lo.skip_supplementary = skip_supplementary; lo.keep_qnames = keep_qnames;
+    Loader *l = new Loader();
+    l->bl = new BatchLoader((BamFile *)bam, lo);
+    return l;
+}
+void mmh_loader_free(void *h) { Loader *l = (Loader *)h; delete l->bl; delete l; }
+int mmh_loader_fill(void *h, mmc_batch_t *b, mmh_stats_t *st, char *err, int errlen) {
+    Loader *l = (Loader *)h;
+    std::string e;
+    int rc = l->bl->fill(b, &l->meta, &e);
+    if (rc < 0) set_err(err, errlen, e);
+    if (st) {
+        st->total_reads = l->meta.stats.total_reads; st->n_recs = l->meta.stats.n_recs;
+        st->total_bytes = l->meta.stats.total_bytes; st->processed_bytes = l->meta.stats.processed_bytes;
+        st->ml_entries = l->meta.stats.ml_entries; st->bases = l->meta.stats.bases;
+    }
+    return rc;
+}
+const char *mmh_loader_qname(void *h, uint32_t i) {
+    Loader *l = (Loader *)h;
+    return i < l->meta.qname_off.size() ? l->meta.qname(i) : "";
+}
+
+void *mmh_fasta_load(const char *path, char *err, int errlen) {
+    Fasta *f = new Fasta();
+    std::string e;
+    if (!read_fasta(path, &f->recs, &e)) { set_err(err, errlen, e); delete f; return nullptr; }
+    return f;
+}
+void mmh_fasta_free(void *h) { delete (Fasta *)h; }
+int mmh_fasta_n(void *h) { return (int)((Fasta *)h)->recs.size(); }
+const char *mmh_fasta_name(void *h, int i) { return ((Fasta *)h)->recs[i].name.c_str(); }
+const char *mmh_fasta_seq(void *h, int i) { return ((Fasta *)h)->recs[i].seq.data(); }
+uint64_t mmh_fasta_len(void *h, int i) { return ((Fasta *)h)->recs[i].seq.size(); }
+
+// "-c" (+ "-m" for freq; NULL/"" = default 0.8 each) -> mmc_mod_t table.  Returns n_mods or -1.
+int mmh_parse_mods(const char *codes, const char *threshes, int subtool, mmc_mod_t *out, int max_out, char *err, int errlen) {
+    std::vector<ModSpec> mods;
+    std::string e;
+    if (!codes || !*codes) codes = "m";
+    if (!parse_mod_codes(codes, &mods, &e)) { set_err(err, errlen, e); return -1; }
+    if (subtool == MMC_FREQ) {
+        std::string t = threshes ? threshes : "";
+        if (t.empty()) for (size_t i = 0; i < mods.size(); ++i) t += i ? ",0.8" : "0.8";
+        if (!parse_mod_threshes(t, &mods, &e)) { set_err(err, errlen, e); return -1; }
+    }
+    std::vector<mmc_mod_t> mm;
+    if (!to_mmc_mods(mods, &mm, &e)) { set_err(err, errlen, e); return -1; }
+    if ((int)mm.size() > max_out) { set_err(err, errlen, "too many modification codes"); return -1; }
+    memcpy(out, mm.data(), sizeof(mmc_mod_t) * mm.size());
+    return (int)mm.size();
+}
+
+// Format freq rows exactly as print_freq_header()+print_freq_output() would; append=0 truncates.
+int mmh_write_freq(const char *path, int bedmethyl, int insertions, int haplotypes, int n_contigs, const char *const *contig_names,
+                   const mmc_freq_rec_t *recs, uint64_t n, int n_codes, const char *const *code_names) {
+    FILE *fp = fopen(path, "w");
+    if (!fp) return -1;
+    OutOpts o; o.bedmethyl = bedmethyl; o.insertions = insertions; o.haplotypes = haplotypes;
+    std::vector<std::string> names(contig_names, contig_names + n_contigs), codes(code_names, code_names + n_codes);
+    print_freq_header(fp, o);
+    print_freq_records(fp, o, names, recs, n, codes);
+    fclose(fp);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+#include "pack.h"
+#include <string.h>
+
+namespace mmh {
+
+static inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+static inline uint64_t up16(uint64_t x) { return (x + (MMC_ALIGN - 1)) & ~(uint64_t)(MMC_ALIGN - 1); }
+
+// (uint8_t)bam_aux2i() of the HP tag, 0 when absent (get_hp_tag, src/mod.c:188-202)
+static uint8_t hp_of(const BamRecord &r) {
+    const uint8_t *s = r.aux_get("HP");
+    if (!s) return 0;
+    int64_t v = 0;
+    switch (*s) {
+    case 'c': v = (int8_t)s[1]; break;
+    case 'C': v = s[1]; break;
+    case 's': v = (int16_t)(s[1] | s[2] << 8); break;
+    case 'S': v = (uint16_t)(s[1] | s[2] << 8); break;
+    case 'i': v = (int32_t)le32(s + 1); break;
+    case 'I': v = le32(s + 1); break;
+    default: v = 0;
+    }
+    return (uint8_t)v;
+}
+
+PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt, BatchMeta *meta) {
+    // ---- filters, in the reference's order (src/minimod.c:260-284)
+    if (rec.flag & 4) return kSkipped;                                   // BAM_FUNMAP
+    if (!opt.allow_secondary && (rec.flag & 256)) return kSkipped;       // BAM_FSECONDARY
+    if (opt.skip_supplementary && (rec.flag & 2048)) return kSkipped;    // BAM_FSUPPLEMENTARY
+    if (rec.l_qseq == 0) return kSkipped;
+    const uint8_t *mm_aux = rec.aux_get("MM");
+    if (!mm_aux || (*mm_aux != 'Z' && *mm_aux != 'H')) return kSkipped;  // get_mm_tag_ptr(), src/mod.c:123-140
+    const char *mm = (const char *)(mm_aux + 1);
+    const size_t mm_len = strlen(mm);
+    // ML must be B,C with len>0 (get_ml_tag, src/mod.c:142-185); otherwise the read is kept with no ML
+    const uint8_t *ml = nullptr;
+    uint32_t ml_len = 0;
+    const uint8_t *ml_aux = rec.aux_get("ML");
+    if (ml_aux && ml_aux[0] == 'B' && ml_aux[1] == 'C' && le32(ml_aux + 2) > 0) { ml_len = le32(ml_aux + 2); ml = ml_aux + 6; }
+
+    // ---- capacity
+    const uint64_t seq_bytes = ((uint64_t)rec.l_qseq + 1) / 2;
+    const uint64_t c0 = up16(b->cigar_used * 4) / 4, s0 = up16(b->seq_used), m0 = up16(b->mm_used), l0 = up16(b->ml_used);
+    if (b->n_reads >= b->max_reads || c0 + rec.n_cigar > b->cigar_cap || s0 + seq_bytes > b->seq_cap ||
+        m0 + mm_len > b->mm_cap || l0 + ml_len > b->ml_cap)
+        return kNoSpace;
+
+    const uint32_t i = b->n_reads;
+    b->tid[i] = rec.tid; b->pos[i] = rec.pos; b->flag[i] = rec.flag;
+    b->l_seq[i] = (uint32_t)rec.l_qseq; b->n_cigar[i] = rec.n_cigar;
+    b->mm_len[i] = (uint32_t)mm_len; b->ml_len[i] = ml_len;
+    b->hp[i] = hp_of(rec);
+    b->cigar_off[i] = c0; b->seq_off[i] = s0; b->mm_off[i] = m0; b->ml_off[i] = l0;
+    memcpy(b->cigar + c0, rec.cigar(), 4 * (size_t)rec.n_cigar);
+    memcpy(b->seq4 + s0, rec.seq(), seq_bytes);
+    memcpy(b->mm + m0, mm, mm_len);
+    if (ml_len) memcpy(b->ml + l0, ml, ml_len);
+    b->cigar_used = c0 + rec.n_cigar; b->seq_used = s0 + seq_bytes; b->mm_used = m0 + mm_len; b->ml_used = l0 + ml_len;
+    b->n_reads = i + 1;
+    if (meta) {
+        meta->stats.ml_entries += ml_len;
+        meta->stats.bases += rec.l_qseq;
+        if (opt.keep_qnames) {
+            meta->qname_off.push_back((uint32_t)meta->qnames.size());
+            meta->qnames.append(rec.qname());
+            meta->qnames.push_back('\0');
+        }
+    }
+    return kPacked;
+}
+
+int BatchLoader::fill(mmc_batch_t *b, BatchMeta *meta, std::string *err) {
+    b->n_reads = 0; b->cigar_used = b->seq_used = b->mm_used = b->ml_used = 0;
+    meta->stats = BatchStats(); meta->qname_off.clear(); meta->qnames.clear();
+    BatchStats &st = meta->stats;
+    // while (n_bam_recs < cap && processed_bytes < batch_size_bases), src/minimod.c:249
+    while (st.n_recs < opt_.batch_size && st.processed_bytes < opt_.batch_size_bases) {
+        if (!has_pending_) {
+            if (eof_) return 0;
+            int rc = bam_->next(&pending_);
+            if (rc == 0) { eof_ = true; return 0; }
+            if (rc < 0) { if (err) *err = "truncated or corrupt BAM record"; return -1; }
+            has_pending_ = true;
+        }
+        PackResult pr = pack_record(pending_, b, opt_, meta);
+        if (pr == kNoSpace) {
+            if (b->n_reads == 0) { if (err) *err = "a single read does not fit the batch buffers; raise -B"; return -1; }
+            return 1;                                   // pinned pools full: end the batch early, keep the record
+        }
+        has_pending_ = false;
+        st.total_reads++; st.total_bytes += pending_.l_data;
+        if (pr == kPacked) { st.n_recs++; st.processed_bytes += pending_.l_data; }
+    }
+    return 1;
+}
+
+}  // namespace mmh
