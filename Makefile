@@ -4,7 +4,7 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v -Xlinker -Bsymbolic
 CXXFLAGS  := -O2 -g -std=c++17 -Wall -fPIC
 CSRC      := minimod_b200/csrc
 HOST      := minimod_b200/host
@@ -23,7 +23,7 @@ $(LIBDIR)/libminimod_cuda.so: $(CSRC)/mmc_api.cu $(CSRC)/mmc_device.cuh $(CSRC)/
 emul: $(EMUL)/_build/libminimod_emul.so
 $(EMUL)/_build/libminimod_emul.so: $(CSRC)/mmc_api.cu $(CSRC)/mmc_device.cuh $(CSRC)/simt.h $(EMUL)/cuda_emul.cpp $(EMUL)/cuda_emul.h include/minimod_cuda.h
 	@mkdir -p $(EMUL)/_build
-	$(CXX) $(CXXFLAGS) -DMMC_EMUL -I $(EMUL) -x c++ $(CSRC)/mmc_api.cu $(EMUL)/cuda_emul.cpp -shared -o $@
+	$(CXX) $(CXXFLAGS) -DMMC_EMUL -I $(EMUL) -x c++ $(CSRC)/mmc_api.cu $(EMUL)/cuda_emul.cpp -shared -Wl,-Bsymbolic -o $@
 
 HOST_SRCS := $(wildcard $(HOST)/*.cpp)
 host: $(LIBDIR)/libminimod_host.so $(BINDIR)/minimod

@@ -218,6 +218,9 @@ int  mmc_view_fetch(mmc_ctx *ctx, mmc_batch_t *batch, const mmc_view_rec_t **rec
  *      Each cell is a uint64: n_called in the low 32 bits, n_mod in the high 32. ------- */
 int  mmc_dense_slice(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end,
                      void **dev_ptr, uint64_t *n_cells);
+/* tell the library that [start,end) of contig tid now holds counts written from outside
+ * (the result of such a reduce), so that finalize scans it */
+int  mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end);
 
 int  mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out);
 int  mmc_reset_timers(mmc_ctx *ctx);

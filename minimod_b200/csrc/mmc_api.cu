@@ -864,6 +864,22 @@ int mmc_dense_slice(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end, voi
     return MMC_OK;
 }
 
+int mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end) {
+    if (!ctx) return MMC_EINVAL;
+    if (tid < 0 || (size_t)tid >= ctx->contigs.size() || !ctx->contigs[tid].loaded) return fail(ctx, MMC_EINVAL, "mmc_dense_touch: bad contig %d", tid);
+    if (start >= end || end > ctx->contigs[tid].len) return fail(ctx, MMC_EINVAL, "mmc_dense_touch: bad range");
+    int rc = mmc_sync(ctx);
+    if (rc != MMC_OK) return rc;
+    const size_t nc = ctx->contigs.size();
+    int32_t lo = 0, hi = 0;
+    CU(ctx, cudaMemcpy(&lo, ctx->d_touch + tid, 4, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(&hi, ctx->d_touch + nc + tid, 4, cudaMemcpyDeviceToHost));
+    lo = std::min<int32_t>(lo, (int32_t)start); hi = std::max<int32_t>(hi, (int32_t)end);
+    CU(ctx, cudaMemcpy(ctx->d_touch + tid, &lo, 4, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_touch + nc + tid, &hi, 4, cudaMemcpyHostToDevice));
+    return MMC_OK;
+}
+
 int mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out) {
     if (!ctx || !out) return MMC_EINVAL;
     *out = ctx->tm;

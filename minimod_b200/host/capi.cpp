@@ -109,4 +109,18 @@ int mmh_write_freq(const char *path, int bedmethyl, int insertions, int haplotyp
     return 0;
 }
 
+// Format the view rows of one batch as print_view_output() would; append=0 writes the header first.
+int mmh_write_view(const char *path, int append, int insertions, int haplotypes, int n_contigs, const char *const *contig_names,
+                   const mmc_batch_t *batch, void *loader, const mmc_view_rec_t *recs, uint64_t n, int n_codes,
+                   const char *const *code_names) {
+    FILE *fp = fopen(path, append ? "a" : "w");
+    if (!fp) return -1;
+    OutOpts o; o.insertions = insertions; o.haplotypes = haplotypes;
+    std::vector<std::string> names(contig_names, contig_names + n_contigs), codes(code_names, code_names + n_codes);
+    if (!append) print_view_header(fp, o);
+    print_view_records(fp, o, names, batch, ((Loader *)loader)->meta, recs, n, codes);
+    fclose(fp);
+    return 0;
+}
+
 }  // extern "C"

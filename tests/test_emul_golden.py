@@ -1,0 +1,29 @@
+"""CPU-only: the product's kernel sources, compiled for the SIMT emulator in tests/kernel_emul, driven
+through the same C ABI + host code as on the GPU, against the reference's golden files.  This is what
+lets `pytest -m "not gpu"` exercise the decode/finalize kernels' logic; the GPU tests repeat it on HBM."""
+import pytest
+
+from golden_runner import TIE_FREE, run_case
+from helpers import GOLDEN_CASES, golden_bytes, sorted_lines
+
+CHR22 = [c for c in GOLDEN_CASES if c[4] == "chr22"]
+CHR1 = [c for c in GOLDEN_CASES if c[4] == "chr1"]
+
+
+@pytest.mark.parametrize("name,sub,args,bam,contig", CHR22 + CHR1, ids=[c[0] for c in CHR22 + CHR1])
+def test_emulated_kernels_reproduce_golden(emul_lib, name, sub, args, bam, contig):
+    out = run_case(emul_lib, sub, args, bam, contig)
+    gold = golden_bytes(name)
+    if name in TIE_FREE:
+        assert out == gold
+    else:
+        assert sorted_lines(out) == sorted_lines(gold)
+
+
+@pytest.mark.parametrize("name", ["test7.tsv", "test5a.tsv", "test2a.tsv", "test17a.tsv"])
+def test_scratch_paths(emul_lib, monkeypatch, name):
+    """Force the global-scratch fallbacks (long CIGARs / long reads) with tiny shared-memory caps."""
+    monkeypatch.setenv("MMC_TEST_SMALL_SMEM", "1")
+    case = [c for c in GOLDEN_CASES if c[0] == name][0]
+    out = run_case(emul_lib, *case[1:])
+    assert sorted_lines(out) == sorted_lines(golden_bytes(name))

@@ -1,0 +1,67 @@
+"""GPU parity, through the C ABI (libminimod_cuda.so loaded in this process) and through the `minimod`
+binary: every golden file of the reference's test.sh that pins this path."""
+import os
+import shlex
+import subprocess
+
+import pytest
+
+from golden_runner import TIE_FREE, run_case
+from helpers import DATA, GOLDEN_CASES, ROOT, golden_bytes, have_ref_bin, pseudo_fasta, run_ref, sorted_lines
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "minimod_b200", "bin", "minimod")
+
+
+@pytest.mark.parametrize("name,sub,args,bam,contig", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_cuda_reproduces_golden(cuda_lib, name, sub, args, bam, contig):
+    out = run_case(cuda_lib, sub, args, bam, contig)
+    gold = golden_bytes(name)
+    if name in TIE_FREE:
+        assert out == gold
+    else:
+        assert sorted_lines(out) == sorted_lines(gold)
+
+
+@pytest.mark.parametrize("name", ["test7.tsv", "test5a.tsv", "test2a.tsv", "test17a.tsv", "test5c.tsv"])
+def test_cuda_scratch_paths(cuda_lib, monkeypatch, name):
+    monkeypatch.setenv("MMC_TEST_SMALL_SMEM", "1")
+    case = [c for c in GOLDEN_CASES if c[0] == name][0]
+    out = run_case(cuda_lib, *case[1:])
+    assert sorted_lines(out) == sorted_lines(golden_bytes(name))
+
+
+@pytest.mark.parametrize("threads", ["32", "64", "256"])
+def test_cuda_cta_sizes(cuda_lib, monkeypatch, threads):
+    monkeypatch.setenv("MMC_DECODE_THREADS", threads)
+    for name in ("test7.tsv", "test8.tsv"):
+        case = [c for c in GOLDEN_CASES if c[0] == name][0]
+        assert sorted_lines(run_case(cuda_lib, *case[1:])) == sorted_lines(golden_bytes(name))
+
+
+@pytest.mark.parametrize("name", ["test7.tsv", "test4.bedmethyl", "test2.tsv", "test12.tsv"])
+def test_cli_binary(name):
+    case = [c for c in GOLDEN_CASES if c[0] == name][0]
+    _, sub, args, bam, contig = case
+    res = subprocess.run([CLI, sub] + shlex.split(args) + [pseudo_fasta(contig), os.path.join(DATA, bam)],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-2000:]
+    if name in TIE_FREE:
+        assert res.stdout == golden_bytes(name)
+    else:
+        assert sorted_lines(res.stdout) == sorted_lines(golden_bytes(name))
+
+
+@pytest.mark.skipif(not have_ref_bin(), reason="oracle/_ref/minimod_ref not present")
+@pytest.mark.parametrize("bam,args", [
+    ("dna_5mC_5hmC_mm_chr22.bam", "-c m[*],h[*]"),          # '.' status blocks: implicit calls
+    ("dna_5mC_5hmC_mm_chr22.bam", "-c m[*],h[*] --insertions"),
+    ("dna_6mA_mm_chr22.bam", "-c a[*]"),
+    ("dna_6mA_mm_chr22.bam", "-c *"),
+])
+def test_cuda_vs_reference_binary_live(cuda_lib, bam, args):
+    fa, path = pseudo_fasta("chr22"), os.path.join(DATA, bam)
+    for sub in ("freq", "view"):
+        ref_out = run_ref(sub, args, fa, path)
+        out = run_case(cuda_lib, sub, args, bam, "chr22")
+        assert sorted_lines(out) == sorted_lines(ref_out)
