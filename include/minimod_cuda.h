@@ -95,6 +95,8 @@ typedef struct {
     int32_t  dense_haps;         /* haplotype values 0..dense_haps-1 get dense strata; 0 -> 4 */
     int32_t  dense_codes;        /* with a wildcard code: dense code slots; 0 -> 8 */
     uint64_t view_capacity;      /* VIEW: records per batch; 0 -> derived from max_bytes */
+    /* optional explicit pool capacities per batch (0 -> derived from max_bytes) */
+    uint64_t cap_cigar_words, cap_seq_bytes, cap_mm_bytes, cap_ml_bytes;
 } mmc_opts_t;
 
 /* A batch in flight.  Replaces the per-read fields of db_t (src/minimod.h:125-160) that

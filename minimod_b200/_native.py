@@ -28,7 +28,9 @@ class MmcOpts(C.Structure):
                 ("mods", C.POINTER(MmcMod)), ("insertions", C.c_int32), ("haplotypes", C.c_int32),
                 ("device", C.c_int32), ("n_slots", C.c_int32), ("max_reads", C.c_uint64),
                 ("max_bytes", C.c_uint64), ("sparse_capacity", C.c_uint64), ("dense_haps", C.c_int32),
-                ("dense_codes", C.c_int32), ("view_capacity", C.c_uint64)]
+                ("dense_codes", C.c_int32), ("view_capacity", C.c_uint64),
+                ("cap_cigar_words", C.c_uint64), ("cap_seq_bytes", C.c_uint64), ("cap_mm_bytes", C.c_uint64),
+                ("cap_ml_bytes", C.c_uint64)]
 
 
 class MmcBatch(C.Structure):
@@ -61,6 +63,10 @@ class MmcTimers(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("decode_ms", C.c_double), ("finalize_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("batches", C.c_uint64), ("reads", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class MmhSynthStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_reads", "bases", "ml_entries", "cigar_ops", "mm_bytes", "ref_span", "seq_bytes")]
 
 
 class MmhStats(C.Structure):
@@ -136,6 +142,13 @@ def _declare_host(lib):
         "mmh_parse_mods": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, P(MmcMod), C.c_int, C.c_char_p, C.c_int]),
         "mmh_write_freq": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_char_p), P(MmcFreqRec),
                                       C.c_uint64, C.c_int, P(C.c_char_p)]),
+        "mmh_synth_new": (vp, [C.c_int, C.c_uint64, C.c_int, P(C.c_char_p), P(C.c_uint32), C.c_double]),
+        "mmh_synth_free": (None, [vp]),
+        "mmh_synth_n_reads": (C.c_uint64, [vp]),
+        "mmh_synth_ref": (vp, [vp, C.c_int, P(C.c_uint64)]),
+        "mmh_synth_write_fasta": (C.c_int, [vp, C.c_char_p]),
+        "mmh_synth_fill": (C.c_int64, [vp, P(MmcBatch), C.c_uint64, C.c_uint64, C.c_int, P(MmhSynthStats)]),
+        "mmh_synth_write_bam": (C.c_int, [vp, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, P(MmhSynthStats)]),
         "mmh_write_view": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_char_p), P(MmcBatch), vp,
                                       P(MmcViewRec), C.c_uint64, C.c_int, P(C.c_char_p)]),
     }

@@ -152,6 +152,10 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     // pool capacities (bytes).  Any pool filling up ends the batch early, which never changes results.
     size_t cap_seq = align_up(o.max_bytes / 2 + 4096, 64), cap_cig = align_up(o.max_bytes / 2 + 4096, 64);
     size_t cap_mm = align_up(o.max_bytes / 2 + 4096, 64), cap_ml = align_up(o.max_bytes / 4 + 4096, 64);
+    if (o.cap_cigar_words) cap_cig = align_up(o.cap_cigar_words * 4, 64);
+    if (o.cap_seq_bytes) cap_seq = align_up(o.cap_seq_bytes, 64);
+    if (o.cap_mm_bytes) cap_mm = align_up(o.cap_mm_bytes, 64);
+    if (o.cap_ml_bytes) cap_ml = align_up(o.cap_ml_bytes, 64);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
     s.o_tid = take(R * 4); s.o_pos = take(R * 4); s.o_lseq = take(R * 4); s.o_ncig = take(R * 4);
