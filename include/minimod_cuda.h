@@ -223,6 +223,8 @@ int  mmc_dense_slice(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end,
 /* tell the library that [start,end) of contig tid now holds counts written from outside
  * (the result of such a reduce), so that finalize scans it */
 int  mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end);
+/* [lo,hi) of contig tid that any submitted read (or mmc_dense_touch) has covered so far; lo>=hi: nothing */
+int  mmc_touched_range(mmc_ctx *ctx, int32_t tid, uint32_t *lo, uint32_t *hi);
 
 int  mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out);
 int  mmc_reset_timers(mmc_ctx *ctx);

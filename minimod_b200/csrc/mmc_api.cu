@@ -884,6 +884,19 @@ int mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end) {
     return MMC_OK;
 }
 
+int mmc_touched_range(mmc_ctx *ctx, int32_t tid, uint32_t *lo, uint32_t *hi) {
+    if (!ctx || !lo || !hi) return MMC_EINVAL;
+    if (tid < 0 || (size_t)tid >= ctx->contigs.size()) return fail(ctx, MMC_EINVAL, "mmc_touched_range: bad contig %d", tid);
+    int rc = mmc_sync(ctx);
+    if (rc != MMC_OK) return rc;
+    const size_t nc = ctx->contigs.size();
+    int32_t l = 0, h = 0;
+    CU(ctx, cudaMemcpy(&l, ctx->d_touch + tid, 4, cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemcpy(&h, ctx->d_touch + nc + tid, 4, cudaMemcpyDeviceToHost));
+    if (l >= h) { *lo = 0; *hi = 0; } else { *lo = (uint32_t)l; *hi = (uint32_t)h; }
+    return MMC_OK;
+}
+
 int mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out) {
     if (!ctx || !out) return MMC_EINVAL;
     *out = ctx->tm;

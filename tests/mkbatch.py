@@ -1,0 +1,40 @@
+"""Hand-built reads for edge-case tests: write BAM-like fields straight into an mmc_batch_t."""
+import ctypes as C
+
+NT16 = "=ACMGRSVTWYHKDBN"
+OPS = "MIDNSHP=XB"
+
+
+def up16(x):
+    return (x + 15) & ~15
+
+
+def add_read(bp, tid, pos, flag, seq, cigar, mm, ml, hp=0):
+    """bp: POINTER(MmcBatch).  cigar: string like '10M2I5M'.  ml: bytes or None."""
+    b = bp.contents
+    i = b.n_reads
+    assert i < b.max_reads
+    ops, num = [], ""
+    for ch in cigar:
+        if ch.isdigit():
+            num += ch
+        else:
+            ops.append((int(num) << 4) | OPS.index(ch)); num = ""
+    c0, s0, m0, l0 = up16(b.cigar_used * 4) // 4, up16(b.seq_used), up16(b.mm_used), up16(b.ml_used)
+    for k, w in enumerate(ops):
+        b.cigar[c0 + k] = w
+    nb = (len(seq) + 1) // 2
+    for k in range(nb):
+        hi = NT16.index(seq[2 * k])
+        lo = NT16.index(seq[2 * k + 1]) if 2 * k + 1 < len(seq) else 0
+        b.seq4[s0 + k] = (hi << 4) | lo
+    mmb = mm.encode()
+    C.memmove(C.addressof(b.mm.contents) + m0, mmb, len(mmb))
+    mlb = bytes(ml or b"")
+    for k, v in enumerate(mlb):
+        b.ml[l0 + k] = v
+    b.tid[i], b.pos[i], b.flag[i], b.hp[i] = tid, pos, flag, hp
+    b.l_seq[i], b.n_cigar[i], b.mm_len[i], b.ml_len[i] = len(seq), len(ops), len(mmb), len(mlb)
+    b.cigar_off[i], b.seq_off[i], b.mm_off[i], b.ml_off[i] = c0, s0, m0, l0
+    b.cigar_used, b.seq_used, b.mm_used, b.ml_used = c0 + len(ops), s0 + nb, m0 + len(mmb), l0 + len(mlb)
+    b.n_reads = i + 1

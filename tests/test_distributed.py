@@ -1,0 +1,81 @@
+"""N>1 host logic on CPU: two gloo ranks, each driving the (emulated) kernels on the reads that start in its
+half of the contig, then the halo exchange of minimod_b200.shard -- the union of the ranks' rows must equal
+the single-process result.  Also the contig partitioner."""
+import os
+import subprocess
+import sys
+
+from helpers import ROOT
+from minimod_b200 import shard
+
+GRCH38_LIKE = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422,
+               135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167,
+               46709983, 50818468, 156040895, 57227415, 16569] + [40000 + 1000 * i for i in range(170)]
+
+
+def test_lpt_partition_balances_grch38():
+    for g in (1, 2, 4, 8):
+        bins, load = shard.lpt_partition(GRCH38_LIKE, g)
+        assert sorted(t for b in bins for t in b) == list(range(len(GRCH38_LIKE)))
+        assert max(load) - min(load) <= max(GRCH38_LIKE)
+        assert max(load) <= sum(GRCH38_LIKE) / g * 1.25 or g == 1
+
+
+def test_region_bounds_cover_contig():
+    b = shard.region_bounds(50818468, 8)
+    assert b[0][0] == 0 and b[-1][1] == 50818468
+    assert all(b[i][1] == b[i + 1][0] for i in range(7))
+    assert shard.owner_of(0, b) == 0 and shard.owner_of(50818467, b) == 7
+
+
+WORKER = r'''
+import ctypes as C, os, sys, pickle
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from minimod_b200 import _native as N, shard
+from minimod_b200.synth import Synth, CONFIG_ARGS
+from parity import Pair
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+lib = N.load_cuda(os.path.join({root!r}, "tests/kernel_emul/_build/libminimod_emul.so"))
+clen = 150000
+s = Synth(3, contigs=(("chrS", clen),), coverage=3.0)
+ca = CONFIG_ARGS[3]
+p, n = s.ref(0)
+ref = C.string_at(p, n)
+bounds = shard.region_bounds(clen, world)
+pair = Pair(lib, "freq", [("chrS", ref)], "m[CG],h[CG]", "0.8,0.7", max_reads=s.n_reads + 8, max_bytes=32 << 20)
+# pack everything, then keep only the reads whose start this rank owns (reads are coordinate sorted)
+full = Pair(lib, "freq", [("chrS", ref)], "m[CG],h[CG]", "0.8,0.7", max_reads=s.n_reads + 8, max_bytes=32 << 20)
+s.fill(full.batch, 0, s.n_reads, 2)
+starts = [full.batch.contents.pos[i] for i in range(full.batch.contents.n_reads)]
+mine = [i for i, st in enumerate(starts) if shard.owner_of(st, bounds) == rank]
+assert mine and mine == list(range(mine[0], mine[-1] + 1))
+s.fill(pair.batch, mine[0], len(mine), 2)
+rc, msg = pair.run_device(); assert rc == 0, msg
+halo = shard.exchange_halos(lib, pair.ctx, 0, bounds, rank, dist, cuda=False)
+rows = pair.device_freq()
+own = [r for r in rows if bounds[rank][0] <= r[1] < bounds[rank][1]]
+gathered = [None] * world
+dist.all_gather_object(gathered, own)
+if rank == 0:
+    rc, msg = full.run_device(); assert rc == 0, msg
+    single = full.device_freq()
+    merged = sorted(r for part in gathered for r in part)
+    assert halo > 0
+    assert merged == single, (len(merged), len(single))
+    print("OK", len(single), "rows; halo", halo)
+dist.destroy_process_group()
+'''
+
+
+def test_region_sharding_two_ranks_gloo(emul_lib, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e.decode()[-3000:]
+    assert b"OK" in outs[0][0]
