@@ -16,6 +16,7 @@
 
 #include "../../include/minimod_cuda.h"
 #include "mmc_device.cuh"
+#include "mmc_decode_warp.cuh"
 
 using namespace mmc;
 
@@ -39,8 +40,10 @@ struct Slot {
     size_t o_cigar, o_seq, o_mm, o_ml;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-    // small device state: [0] err (u64), [1] view_n (u64), [2] work counter (u32)
+    // small device state: [0] err (u64), [1] view_n (u64), then u32: [4] work counter of k_decode_warp,
+    // [5] number of deferred reads, [6] work counter of k_decode
     unsigned long long *d_state = nullptr;
+    uint32_t *d_defer = nullptr;               // reads k_decode_warp left to k_decode
     unsigned long long *h_state = nullptr;     // pinned mirror
     ViewDev *d_view = nullptr;
     uint32_t *d_scratch = nullptr;
@@ -68,6 +71,9 @@ struct mmc_ctx {
     std::vector<Slot> slots;
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
+    int warp_path = 1, w_ctas_per_sm = 1;      // k_decode_warp first, k_decode for what it defers
+    int w_minb = 3;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
+    uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
     int n_code_slots = 1, n_hap_slots = 1, wild_req = -1;
     ReqMod *d_req = nullptr;
     unsigned long long *d_code_keys = nullptr;
@@ -173,6 +179,7 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaEventCreate(&s.ev_k0)); CU(ctx, cudaEventCreate(&s.ev_k1));
     CU(ctx, cudaMalloc((void **)&s.d_state, 64));
     CU(ctx, cudaMallocHost((void **)&s.h_state, 64));
+    CU(ctx, cudaMalloc((void **)&s.d_defer, sizeof(uint32_t) * std::max<size_t>(1, R)));
     if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
     mmc_batch_t &b = s.pub;
     memset(&b, 0, sizeof(b));
@@ -226,9 +233,9 @@ int upload(mmc_ctx *ctx, Slot &s) {
 int launch_decode(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const uint32_t n = s.n_reads_submitted;
-    // reset the slot's device state: err = ~0, view_n = 0, work counter = 0
-    s.h_state[0] = ~0ull; s.h_state[1] = 0; s.h_state[2] = 0;
-    CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 24, cudaMemcpyHostToDevice, s.stream));
+    // reset the slot's device state: err = ~0, view_n = 0, work counters and deferred count = 0
+    s.h_state[0] = ~0ull; s.h_state[1] = 0; s.h_state[2] = 0; s.h_state[3] = 0;
+    CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 32, cudaMemcpyHostToDevice, s.stream));
     if (n == 0) { s.in_flight = true; s.timed = false; return MMC_OK; }
 
     uint32_t max_cig = 0, max_l = 0;
@@ -271,14 +278,30 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     P.err = s.d_state;
     P.scratch = per_cta ? s.d_scratch : nullptr;
     P.scratch_words_per_cta = per_cta; P.scratch_cig_words = cig_words;
-    P.work_counter = (uint32_t *)(s.d_state + 2);
+    uint32_t *st32 = (uint32_t *)s.d_state;
+    P.work_counter = st32 + 4;
     P.cig_smem_cap = ctx->cig_smem_cap; P.bitmap_smem_words = ctx->bitmap_smem_words; P.idx_smem_cap = ctx->idx_smem_cap;
 
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    if (ctx->warp_path) {
+        // fast path: one warp per read; reads that do not fit a warp's shared-memory arena go to the list
+        WarpParams W;
+        W.arena_bytes = ctx->w_arena_bytes; W.defer_list = s.d_defer; W.defer_n = st32 + 5;
+        const uint64_t warps = n;                             // one warp per read, persistent above the resident limit
+        unsigned wgrid = (unsigned)std::min<uint64_t>((warps + kWThreads / 32 - 1) / (kWThreads / 32), (uint64_t)ctx->sm_count * ctx->w_ctas_per_sm);
+        if (wgrid == 0) wgrid = 1;
+        const size_t wsmem = (size_t)ctx->w_arena_bytes * (kWThreads / 32);
+        if (ctx->w_minb == 2) MMC_LAUNCH_SMEM(k_decode_warp<2>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
+        else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM(k_decode_warp<3>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
+        else MMC_LAUNCH_SMEM(k_decode_warp<4>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 1;
+        P.read_list = s.d_defer; P.read_list_n = st32 + 5; P.work_counter = st32 + 6;
+    }
     MMC_LAUNCH(k_decode, grid, (unsigned)ctx->threads, s.stream, P);
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(s.ev_k1, s.stream));
-    CU(ctx, cudaMemcpyAsync(s.h_state, s.d_state, 16, cudaMemcpyDeviceToHost, s.stream));
+    CU(ctx, cudaMemcpyAsync(s.h_state, s.d_state, 32, cudaMemcpyDeviceToHost, s.stream));
     ctx->tm.kernel_launches += 1;
     ctx->tm.batches += 1;
     ctx->tm.reads += n;
@@ -298,6 +321,8 @@ int wait_slot(mmc_ctx *ctx, Slot &s) {
     if (s.timed) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) ctx->tm.decode_ms += ms;
+        ctx->tm.deferred_reads += ((const uint32_t *)s.h_state)[5];
+        s.timed = false;
     }
     if (s.n_reads_submitted && s.h_state[0] != ~0ull) {
         uint32_t read = (uint32_t)(s.h_state[0] >> 32), code = (uint32_t)(s.h_state[0] & 0xffffffffu);
@@ -347,6 +372,15 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     if (const char *e = getenv("MMC_TEST_SMALL_SMEM")) {     // test hook: force the global-scratch paths
         if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
     }
+    if (const char *e = getenv("MMC_DECODE_PATH")) {         // "general": CTA-per-read kernel only (test hook / A-B timing)
+        if (!strcmp(e, "general")) ctx->warp_path = 0;
+    }
+    if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->w_minb = v; }   // tuning
+    ctx->w_arena_bytes = ctx->w_minb == 2 ? 14336u : ctx->w_minb == 3 ? 9600u : 7040u;   // (228 KB / MINB - 1 KB) / 8 warps
+    if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
+        long v = atol(e);
+        if (v >= (long)sizeof(WFixed) + 256 && v <= 27 * 1024) ctx->w_arena_bytes = (uint32_t)(v & ~15l);
+    }
 
 #define CUC(call)                                                                                            \
     do {                                                                                                     \
@@ -365,6 +399,21 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     int occ = 1;
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, ctx->threads, 0));
     ctx->ctas_per_sm = occ < 1 ? 1 : occ;
+    {
+        const size_t smem = (size_t)ctx->w_arena_bytes * (kWThreads / 32);
+        int wocc = 1;
+        if (ctx->w_minb == 2) {
+            CUC(cudaFuncSetAttribute(k_decode_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, k_decode_warp<2>, kWThreads, smem));
+        } else if (ctx->w_minb == 3) {
+            CUC(cudaFuncSetAttribute(k_decode_warp<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, k_decode_warp<3>, kWThreads, smem));
+        } else {
+            CUC(cudaFuncSetAttribute(k_decode_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, k_decode_warp<4>, kWThreads, smem));
+        }
+        ctx->w_ctas_per_sm = wocc < 1 ? 1 : wocc;
+    }
 
     // ---- -c entries -> device tables
     std::vector<ReqMod> req(o.n_mods);
@@ -395,6 +444,13 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
             }
         }
         memcpy(r.lut, m.call_lut, 256);
+        r.fast_ctx = r.ctx_len >= 1 && r.ctx_len <= 8;
+        for (int k = 0; k < r.ctx_len && r.fast_ctx; ++k) {
+            auto code2 = [](uint8_t c) -> int { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; };
+            int a = code2(r.pat[k]), b = code2(r.pat_rc[k]);
+            if (a < 0 || b < 0) { r.fast_ctx = 0; break; }
+            r.pat2 |= (uint32_t)a << (2 * k); r.pat2_rc |= (uint32_t)b << (2 * k);
+        }
     }
     CUC(cudaMalloc((void **)&ctx->d_req, sizeof(ReqMod) * req.size()));
     CUC(cudaMemcpy(ctx->d_req, req.data(), sizeof(ReqMod) * req.size(), cudaMemcpyHostToDevice));
@@ -449,6 +505,7 @@ void mmc_destroy(mmc_ctx *ctx) {
         if (s.d_state) cudaFree(s.d_state);
         if (s.h_state) cudaFreeHost(s.h_state);
         if (s.d_view) cudaFree(s.d_view);
+        if (s.d_defer) cudaFree(s.d_defer);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.ev_h0) cudaEventDestroy(s.ev_h0);
         if (s.ev_h1) cudaEventDestroy(s.ev_h1);
@@ -496,8 +553,10 @@ int mmc_ref_add(mmc_ctx *ctx, int32_t tid, const char *seq, uint32_t len) {
         return fail(ctx, MMC_ENOMEM, "contig %s needs %.1f GB of HBM for its packed reference and dense count array (%zu cells per position) but %.1f GB are free; shard contigs across GPUs or lower dense_haps/dense_codes",
                     c.name.c_str(), need / 1e9, spp, free_b / 1e9);
     uint32_t *ref2 = nullptr, *excm = nullptr;
-    CU(ctx, cudaMalloc((void **)&ref2, std::max<size_t>(8, n32 * 8)));
-    CU(ctx, cudaMalloc((void **)&excm, std::max<size_t>(4, n32 * 4)));
+    CU(ctx, cudaMalloc((void **)&ref2, n32 * 8 + 16));       // + slack: windows are read as two adjacent words
+    CU(ctx, cudaMalloc((void **)&excm, n32 * 4 + 16));
+    CU(ctx, cudaMemsetAsync(ref2 + n32 * 2, 0, 16, ctx->fin_stream));
+    CU(ctx, cudaMemsetAsync(excm + n32, 0, 16, ctx->fin_stream));
     c.dev.ref2 = ref2; c.dev.excm = excm; c.dev.len = len;
     if (ctx->opts.subtool == MMC_FREQ) {
         CU(ctx, cudaMalloc((void **)&c.dev.cells, std::max<size_t>(8, (size_t)len * spp * 8)));

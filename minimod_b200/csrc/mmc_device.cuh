@@ -60,6 +60,8 @@ struct ReqMod {                       // one -c entry on the device (modcodem_t,
     uint8_t pat[32];                  // context, forward orientation (chars A,C,G,T,N)
     uint8_t pat_rc[32];               // reverse-complemented context (src/ref.c:183-194)
     uint8_t lut[256];                 // bit0 called, bit1 mod
+    uint32_t fast_ctx;                // context is 1..8 bases of A/C/G/T: window test on the 2-bit reference
+    uint32_t pat2, pat2_rc;           // context / its reverse complement, 2 bits per base, first base lowest
 };
 
 struct ContigDev {                    // per header contig (ref_t, src/ref.h:36-41, + its dense count array)
@@ -136,6 +138,8 @@ struct DecodeParams {
     unsigned long long scratch_words_per_cta;
     uint32_t scratch_cig_words;       // words reserved for each of cq / cr
     uint32_t *work_counter;           // dynamic read scheduler
+    const uint32_t *read_list;        // k_decode only: reads to process (nullptr: 0..n_reads-1)
+    const uint32_t *read_list_n;      //   and how many (device memory, written by k_decode_warp)
     // test hooks: shrink the shared-memory capacities to force the scratch paths
     int32_t cig_smem_cap;
     int32_t bitmap_smem_words;
@@ -551,7 +555,11 @@ __global__ void __launch_bounds__(kMaxThreads) k_decode(DecodeParams P) {
     for (;;) {
         // ---- dynamic read scheduler
         __syncthreads();
-        if (t == 0) rs->next_read = atomicAdd(P.work_counter, 1u);
+        if (t == 0) {
+            uint32_t nx = atomicAdd(P.work_counter, 1u);
+            if (P.read_list) nx = nx < *P.read_list_n ? P.read_list[nx] : 0xffffffffu;   // reads deferred by k_decode_warp
+            rs->next_read = nx;
+        }
         __syncthreads();
         const uint32_t r = rs->next_read;
         if (r >= P.n_reads) break;

@@ -12,10 +12,17 @@
 #include "cuda_emul.h"
 #define MMC_LAUNCH(kernel, grid, block, stream, ...) \
     ::cuda_emul::launch((grid), (block), [=]() { kernel(__VA_ARGS__); })
+#define MMC_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    ::cuda_emul::launch((grid), (block), [=]() { kernel(__VA_ARGS__); })
+// dynamic shared memory: one static buffer of the hardware maximum (CTAs run one after another)
+#define MMC_DYN_SMEM(type, name) static type name[(228 * 1024) / sizeof(type)] __attribute__((aligned(16)))
 #else
 #include <cuda_runtime.h>
 #define MMC_LAUNCH(kernel, grid, block, stream, ...) \
     kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define MMC_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MMC_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
 #endif

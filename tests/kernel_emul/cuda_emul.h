@@ -67,6 +67,12 @@ static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u));
+}
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
+    return (uint32_t)((((((uint64_t)hi) << 32) | lo) << (sh & 31u)) >> 32);
+}
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 
 template <class T> static inline T emul_atomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
@@ -115,5 +121,7 @@ cudaError_t cudaEventElapsedTime(float *, cudaEvent_t, cudaEvent_t);
 cudaError_t cudaGetLastError();
 const char *cudaGetErrorString(cudaError_t);
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 #endif
