@@ -15,13 +15,13 @@ EMUL      := tests/kernel_emul
 all: lib host oracle emul emul-cli
 
 lib: $(LIBDIR)/libminimod_cuda.so
-$(LIBDIR)/libminimod_cuda.so: $(CSRC)/mmc_api.cu $(CSRC)/mmc_device.cuh $(CSRC)/simt.h include/minimod_cuda.h
+$(LIBDIR)/libminimod_cuda.so: $(wildcard $(CSRC)/*) include/minimod_cuda.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/mmc_api.cu 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 	@grep -E "registers|spill|error" $(LIBDIR)/ptxas.log | head -20 || true
 
 emul: $(EMUL)/_build/libminimod_emul.so
-$(EMUL)/_build/libminimod_emul.so: $(CSRC)/mmc_api.cu $(CSRC)/mmc_device.cuh $(CSRC)/simt.h $(EMUL)/cuda_emul.cpp $(EMUL)/cuda_emul.h include/minimod_cuda.h
+$(EMUL)/_build/libminimod_emul.so: $(wildcard $(CSRC)/*) $(EMUL)/cuda_emul.cpp $(EMUL)/cuda_emul.h include/minimod_cuda.h
 	@mkdir -p $(EMUL)/_build
 	$(CXX) $(CXXFLAGS) -DMMC_EMUL -I $(EMUL) -x c++ $(CSRC)/mmc_api.cu $(EMUL)/cuda_emul.cpp -shared -Wl,-Bsymbolic -o $@
 

@@ -290,7 +290,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         const uint64_t warps = n;                             // one warp per read, persistent above the resident limit
         unsigned wgrid = (unsigned)std::min<uint64_t>((warps + kWThreads / 32 - 1) / (kWThreads / 32), (uint64_t)ctx->sm_count * ctx->w_ctas_per_sm);
         if (wgrid == 0) wgrid = 1;
-        const size_t wsmem = (size_t)ctx->w_arena_bytes * (kWThreads / 32);
+        const size_t wsmem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
         if (ctx->w_minb == 2) MMC_LAUNCH_SMEM(k_decode_warp<2>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
         else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM(k_decode_warp<3>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
         else MMC_LAUNCH_SMEM(k_decode_warp<4>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
@@ -376,7 +376,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (!strcmp(e, "general")) ctx->warp_path = 0;
     }
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->w_minb = v; }   // tuning
-    ctx->w_arena_bytes = ctx->w_minb == 2 ? 14336u : ctx->w_minb == 3 ? 9600u : 7040u;   // (228 KB / MINB - 1 KB) / 8 warps
+    ctx->w_arena_bytes = ctx->w_minb == 2 ? 14208u : ctx->w_minb == 3 ? 9344u : 6912u;   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
         long v = atol(e);
         if (v >= (long)sizeof(WFixed) + 256 && v <= 27 * 1024) ctx->w_arena_bytes = (uint32_t)(v & ~15l);
@@ -400,7 +400,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, ctx->threads, 0));
     ctx->ctas_per_sm = occ < 1 ? 1 : occ;
     {
-        const size_t smem = (size_t)ctx->w_arena_bytes * (kWThreads / 32);
+        const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
         int wocc = 1;
         if (ctx->w_minb == 2) {
             CUC(cudaFuncSetAttribute(k_decode_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

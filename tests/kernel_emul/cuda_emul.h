@@ -24,6 +24,8 @@
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
+#define __grid_constant__
+#define __noinline__ __attribute__((noinline))
 
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
