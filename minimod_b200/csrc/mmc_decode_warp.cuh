@@ -80,7 +80,8 @@ struct WFixed {                              // fixed part of a warp's arena
     WBlock   blk[kWBlocks];
     uint4    text[32 + 1];                   // the tile's text, chunk i at text[i] (+ one spill-over chunk)
     uint32_t em[32];                         // per chunk: terminator mask (',' or block end) of its 32 following bytes
-    uint32_t rank[kWTokCap];                 // per token of the tile: byte offset in text, then its base rank
+    uint32_t rank[kWTokCap];                 // per token of the tile: byte offset in text -> base rank -> read position q
+    int32_t  refp[kWTokCap];                 // per call of the tile: reference position (aln[q]) or -1
 };
 
 struct WarpParams {
@@ -204,28 +205,35 @@ __device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, const uint32_t
 // ---------------------------------------------------------------------------------------
 // bases_pos[cls][k] (src/mod.c:977-981): BAM position of the k-th base of the indexed class
 // ---------------------------------------------------------------------------------------
+// probe: index entry + vector that hold class rank k; rem = rank of k inside the vector
+struct SelProbe { uint32_t u, rem; uint4 v; };
 template <bool C0>
-__device__ __forceinline__ uint32_t w_select(const WState &S, const uint32_t *flex, uint32_t pat, uint32_t k) {
+__device__ __forceinline__ SelProbe w_select_probe(const WState &S, const uint32_t *flex, uint32_t pat, uint32_t k) {
     const uint32_t *idx = flex + S.o_idx;
     uint32_t e = flex[S.o_rd + (k >> S.rshift)];                 // entry of rank (k >> rshift) << rshift: at or before k's
     uint32_t nxt = idx[e + 1u];
     while (nxt <= k) { ++e; nxt = idx[e + 1u]; }                 // few steps: 2^rshift ranks span few entries
-    uint32_t rem = k - idx[e];
+    SelProbe p;
+    p.rem = k - idx[e];
     const uint32_t ishift = S.ishift;
     const uint8_t *seq = S.seq;
-    uint32_t u = e << ishift;
-    uint4 v = ld16(seq + (size_t)u * 16u);
+    p.u = e << ishift;
+    p.v = ld16(seq + (size_t)p.u * 16u);
     if (ishift != 0u) {
         for (;;) {                                               // at most 2^ishift vectors
-            uint32_t c = count_u4<C0>(v, pat);
-            if (rem < c) break;
-            rem -= c; ++u;
-            v = ld16(seq + (size_t)u * 16u);
+            uint32_t c = count_u4<C0>(p.v, pat);
+            if (p.rem < c) break;
+            p.rem -= c; ++p.u;
+            p.v = ld16(seq + (size_t)p.u * 16u);
         }
     }
-    const uint32_t f0 = class_flags<C0>(v.x, pat), f1 = class_flags<C0>(v.y, pat), f2 = class_flags<C0>(v.z, pat), f3 = class_flags<C0>(v.w, pat);
+    return p;
+}
+template <bool C0>
+__device__ __forceinline__ uint32_t w_select_resolve(const SelProbe &p, uint32_t pat) {
+    const uint32_t f0 = class_flags<C0>(p.v.x, pat), f1 = class_flags<C0>(p.v.y, pat), f2 = class_flags<C0>(p.v.z, pat), f3 = class_flags<C0>(p.v.w, pat);
     const uint32_t s0 = (uint32_t)__popc(f0), s1 = s0 + (uint32_t)__popc(f1), s2 = s1 + (uint32_t)__popc(f2);
-    uint32_t f = f0, wsel = 0, sub = 0;
+    uint32_t rem = p.rem, f = f0, wsel = 0, sub = 0;
     if (rem >= s0) { f = f1; wsel = 1; sub = s0; }
     if (rem >= s1) { f = f2; wsel = 2; sub = s1; }
     if (rem >= s2) { f = f3; wsel = 3; sub = s2; }
@@ -234,7 +242,7 @@ __device__ __forceinline__ uint32_t w_select(const WState &S, const uint32_t *fl
     c = (uint32_t)__popc(f & 0xffffu);  if (rem >= c) { rem -= c; f >>= 16; off = 4; }
     c = (uint32_t)__popc(f & 0xffu);    if (rem >= c) { rem -= c; f >>= 8; off += 2; }
     off += (rem != 0u || !(f & 0x80u)) ? 1u : 0u;                // bit 7 = the byte's first base
-    return u * 32u + wsel * 8u + off;
+    return p.u * 32u + wsel * 8u + off;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -308,23 +316,20 @@ __device__ __noinline__ void w_emit_view(const DecodeParams &P, uint32_t r, int3
     }
 }
 
-// Everything after "base q of the read is a call" (SURVEY.md A.4-A.8); see process_call().
+// Everything after "base q of the read is a call and maps to ref_pos" (SURVEY.md A.5-A.8); see process_call().
 //   rd_code  2-bit code of the read base when the block's class pins it (C,G,T), else 4
-__device__ __forceinline__ void w_call(const DecodeParams &P, const WState &S, WFixed *wf, const uint32_t *flex, const uint8_t *s_lut,
-                                       const WBlock *bd, uint32_t blk_ord, uint32_t q, bool implicit, uint32_t cidx,
-                                       uint32_t ml_base, uint32_t rd_code) {
-    AlnHit h = w_cigar_lookup(S, flex, q);
-    int32_t ref_pos = h.aln;
-    if (P.insertions && ref_pos < 0) {
-        if (implicit && S.rev) ref_pos = w_cigar_lookup(S, flex, S.L - 1u - q).ins;    // Q9 (src/mod.c:1234,1314)
-        else ref_pos = h.ins;
-    }
-    if (ref_pos < 0) return;                                      // src/mod.c:1127,1237,1317
-    const uint32_t ins_off = P.insertions ? h.insoff : 0u;
+__device__ __forceinline__ void w_call_at(const DecodeParams &P, const WState &S, WFixed *wf, const uint8_t *s_lut,
+                                          const WBlock *bd, uint32_t blk_ord, uint32_t q, int32_t ref_pos, uint32_t ins_off,
+                                          bool implicit, uint32_t cidx, uint32_t ml_base, uint32_t rd_code) {
     const uint32_t K = bd->K, is_n = bd->is_n;
     for (uint32_t m = 0; m < K; ++m) {
         const WCode cd = bd->code[m];
         if (cd.ri < 0) continue;                                  // src/mod.c:1157
+        uint32_t prob = 0, is_mod = 0;
+        if (!implicit) {                                          // issued first: independent of the context test
+            const unsigned long long ml_idx = (unsigned long long)ml_base + (unsigned long long)cidx * K + m;
+            if (ml_idx < S.ml_len) prob = S.ml[ml_idx]; else prob = 0x100u;
+        }
         if (cd.ctx_mode != kCtxNone) {                            // src/mod.c:1162-1172
             uint32_t refcode = 0;
             int32_t in = cd.ctx_mode == kCtxFast ? ctx_fast(S.ref2, S.excm, S.ref_len, (uint32_t)ref_pos, cd.ctx_len, cd.pat2, refcode) : -1;
@@ -342,12 +347,7 @@ __device__ __forceinline__ void w_call(const DecodeParams &P, const WState &S, W
                 }
             }
         }
-        uint32_t prob = 0, is_mod = 0;
-        if (!implicit) {
-            const unsigned long long ml_idx = (unsigned long long)ml_base + (unsigned long long)cidx * K + m;
-            if (ml_idx >= S.ml_len) { w_raise(wf, kErrMLIndex); return; }          // src/mod.c:1174
-            prob = S.ml[ml_idx];
-        }
+        if (prob > 0xffu) { w_raise(wf, kErrMLIndex); return; }   // src/mod.c:1174
         if (P.subtool == 1) {                                     // FREQ
             if (!implicit) {
                 const uint32_t f = cd.ri < kWLutSlots ? s_lut[cd.ri * 256 + prob] : P.req[cd.ri].lut[prob];   // src/mod.c:1181-1191
@@ -363,6 +363,20 @@ __device__ __forceinline__ void w_call(const DecodeParams &P, const WState &S, W
                         cd.outc, prob);
         }
     }
+}
+
+// "base q of the read is a call" (SURVEY.md A.4): read position -> reference position, then the above
+__device__ __forceinline__ void w_call(const DecodeParams &P, const WState &S, WFixed *wf, const uint32_t *flex, const uint8_t *s_lut,
+                                       const WBlock *bd, uint32_t blk_ord, uint32_t q, bool implicit, uint32_t cidx,
+                                       uint32_t ml_base, uint32_t rd_code) {
+    AlnHit h = w_cigar_lookup(S, flex, q);
+    int32_t ref_pos = h.aln;
+    if (P.insertions && ref_pos < 0) {
+        if (implicit && S.rev) ref_pos = w_cigar_lookup(S, flex, S.L - 1u - q).ins;    // Q9 (src/mod.c:1234,1314)
+        else ref_pos = h.ins;
+    }
+    if (ref_pos < 0) return;                                      // src/mod.c:1127,1237,1317
+    w_call_at(P, S, wf, s_lut, bd, blk_ord, q, ref_pos, P.insertions ? h.insoff : 0u, implicit, cidx, ml_base, rd_code);
 }
 
 // commas (or any byte c) of 16 text bytes as a 16-bit mask (bit i <-> byte i)
@@ -730,35 +744,73 @@ __device__ __noinline__ uint32_t w_tile_ranks(WFixed *wf, uint32_t tb, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 4 (per text tile): the explicit calls whose ranks are in wf->rank[0..n): the hot loop
+// phase 4 (per text tile): the explicit calls whose ranks are in wf->rank[0..n).  Three passes
+// staged through shared memory so that each is a short loop with independent iterations:
+//   select  base rank -> read position q            (bases_pos[][], src/mod.c:1102-1113)
+//   map     q -> reference position                 (aln[], src/mod.c:1122)
+//   update  context test, ML threshold, count cell  (src/mod.c:1140-1199)
 // ---------------------------------------------------------------------------------------
+constexpr uint32_t kNoCall = 0xffffffffu;
+
 template <bool C0>
-__device__ __forceinline__ void w_tile_calls_t(const DecodeParams &P, WFixed *wf, uint32_t *flex, const uint8_t *s_lut, uint32_t jb,
-                                               uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
+__device__ __forceinline__ void w_pass_select(WFixed *wf, uint32_t *flex, uint32_t pat, uint32_t n, uint32_t need_bm, uint32_t lane) {
     const WState &S = wf->st;
-    const WBlock *bd = &wf->blk[jb];
-    const uint32_t cls = bd->cls, is_n = bd->is_n, need_bm = bd->dot;
-    const uint32_t pat = class_pat(cls), rd_code = cls >= 1u && cls <= 3u ? cls : 4u;
-    const uint32_t L = S.L, rev = S.rev, cnt_cls = S.cnt_cls;
+    const uint32_t rev = S.rev, cnt_cls = S.cnt_cls;
     uint32_t *bm = flex + S.o_bm;
-    for (uint32_t c = lane; c < n; c += 32u) {
-        const uint32_t rank = wf->rank[c];
-        uint32_t q;
-        if (is_n) {                                               // src/mod.c:1102-1107
-            if (rank >= L) { w_raise(wf, kErrMMRank); continue; }
-            q = rev ? L - 1u - rank : rank;
-        } else {                                                  // src/mod.c:1109-1113
-            if (rank >= cnt_cls) { w_raise(wf, kErrMMRank); continue; }
-            q = w_select<C0>(S, flex, pat, rev ? cnt_cls - 1u - rank : rank);
+    for (uint32_t c = lane; c < n; c += 64u) {                    // two calls per lane in flight
+        const uint32_t c1 = c + 32u;
+        const bool have1 = c1 < n;
+        const uint32_t r0 = wf->rank[c], r1 = have1 ? wf->rank[c1] : 0u;
+        const bool ok0 = r0 < cnt_cls, ok1 = have1 && r1 < cnt_cls;
+        if (!ok0 || (have1 && !ok1)) w_raise(wf, kErrMMRank);     // src/mod.c:1116
+        SelProbe p0, p1;
+        if (ok0) p0 = w_select_probe<C0>(S, flex, pat, rev ? cnt_cls - 1u - r0 : r0);
+        if (ok1) p1 = w_select_probe<C0>(S, flex, pat, rev ? cnt_cls - 1u - r1 : r1);
+        if (need_bm) {
+            if (ok0) atomicOr(&bm[r0 >> 5], 1u << (r0 & 31u));
+            if (ok1) atomicOr(&bm[r1 >> 5], 1u << (r1 & 31u));
         }
-        if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
-        w_call(P, S, wf, flex, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
+        wf->rank[c] = ok0 ? w_select_resolve<C0>(p0, pat) : kNoCall;
+        if (have1) wf->rank[c1] = ok1 ? w_select_resolve<C0>(p1, pat) : kNoCall;
     }
 }
+
 __device__ __noinline__ void w_tile_calls(const DecodeParams &P, WFixed *wf, uint32_t *flex, const uint8_t *s_lut, uint32_t jb,
                                           uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
-    if (wf->blk[jb].cls == 0u) w_tile_calls_t<true>(P, wf, flex, s_lut, jb, n, cidx0, ml_base, lane);
-    else w_tile_calls_t<false>(P, wf, flex, s_lut, jb, n, cidx0, ml_base, lane);
+    const WState &S = wf->st;
+    const WBlock *bd = &wf->blk[jb];
+    const uint32_t cls = bd->cls, need_bm = bd->dot;
+    const uint32_t pat = class_pat(cls), rd_code = cls >= 1u && cls <= 3u ? cls : 4u;
+    // ---- select
+    if (bd->is_n) {                                               // src/mod.c:1102-1107
+        const uint32_t L = S.L, rev = S.rev;
+        uint32_t *bm = flex + S.o_bm;
+        for (uint32_t c = lane; c < n; c += 32u) {
+            const uint32_t rank = wf->rank[c];
+            if (rank >= L) { w_raise(wf, kErrMMRank); wf->rank[c] = kNoCall; continue; }
+            if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
+            wf->rank[c] = rev ? L - 1u - rank : rank;
+        }
+    } else if (cls == 0u) w_pass_select<true>(wf, flex, pat, n, need_bm, lane);
+    else w_pass_select<false>(wf, flex, pat, n, need_bm, lane);
+    if (P.insertions) {                                           // ins[] fall-back and ins_offset: fused map + update
+        for (uint32_t c = lane; c < n; c += 32u) {
+            const uint32_t q = wf->rank[c];
+            if (q != kNoCall) w_call(P, S, wf, flex, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
+        }
+        return;
+    }
+    // ---- map
+    for (uint32_t c = lane; c < n; c += 32u) {
+        const uint32_t q = wf->rank[c];
+        wf->refp[c] = q != kNoCall ? w_cigar_lookup(S, flex, q).aln : -1;
+    }
+    // ---- update
+    for (uint32_t c = lane; c < n; c += 32u) {
+        const int32_t ref_pos = wf->refp[c];
+        if (ref_pos < 0) continue;                                // src/mod.c:1127
+        w_call_at(P, S, wf, s_lut, bd, jb, wf->rank[c], ref_pos, 0u, false, cidx0 + c, ml_base, rd_code);
+    }
 }
 
 // implicit calls of a '.' block (src/mod.c:1203-1367): every base of the class whose rank is not
