@@ -175,6 +175,7 @@ typedef struct {
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     uint64_t deferred_reads; /* reads the warp-per-read kernel handed to the general CTA-per-read kernel */
+    uint64_t flat_deferred_reads; /* reads the flat kernel chain handed to the warp-per-read kernel */
 } mmc_timers_t;
 
 /* ---- lifecycle: replaces init_core()/free_core() (src/minimod.c:51-161) -------------- */

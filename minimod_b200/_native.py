@@ -62,7 +62,8 @@ class MmcViewRec(C.Structure):
 class MmcTimers(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("decode_ms", C.c_double), ("finalize_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("batches", C.c_uint64), ("reads", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("deferred_reads", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("deferred_reads", C.c_uint64),
+                ("flat_deferred_reads", C.c_uint64)]
 
 
 class MmhSynthStats(C.Structure):

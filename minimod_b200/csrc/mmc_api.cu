@@ -17,6 +17,7 @@
 #include "../../include/minimod_cuda.h"
 #include "mmc_device.cuh"
 #include "mmc_decode_warp.cuh"
+#include "mmc_decode_flat.cuh"
 
 using namespace mmc;
 
@@ -44,6 +45,10 @@ struct Slot {
     // [5] number of deferred reads, [6] work counter of k_decode
     unsigned long long *d_state = nullptr;
     uint32_t *d_defer = nullptr;               // reads k_decode_warp left to k_decode
+    uint32_t *d_defer_flat = nullptr;          // reads the flat kernels left to k_decode_warp
+    WRead *d_reads = nullptr;                  // flat path: per-read state
+    uint32_t *d_pool = nullptr; size_t pool_words = 0;      // flat path: scratch pool
+    FlatTile *d_tiles = nullptr; size_t tile_cap = 0;       // flat path: text tiles
     unsigned long long *h_state = nullptr;     // pinned mirror
     ViewDev *d_view = nullptr;
     uint32_t *d_scratch = nullptr;
@@ -71,7 +76,8 @@ struct mmc_ctx {
     std::vector<Slot> slots;
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
-    int warp_path = 1, w_ctas_per_sm = 1;      // k_decode_warp first, k_decode for what it defers
+    int flat_path = 1;                         // the flat kernel chain first (mmc_decode_flat.cuh)
+    int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
     int w_minb = 3;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
     uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
     int n_code_slots = 1, n_hap_slots = 1, wild_req = -1;
@@ -177,8 +183,10 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreate(&s.ev_h0)); CU(ctx, cudaEventCreate(&s.ev_h1));
     CU(ctx, cudaEventCreate(&s.ev_k0)); CU(ctx, cudaEventCreate(&s.ev_k1));
-    CU(ctx, cudaMalloc((void **)&s.d_state, 64));
-    CU(ctx, cudaMallocHost((void **)&s.h_state, 64));
+    CU(ctx, cudaMalloc((void **)&s.d_state, 128));
+    CU(ctx, cudaMallocHost((void **)&s.h_state, 128));
+    CU(ctx, cudaMalloc((void **)&s.d_defer_flat, sizeof(uint32_t) * std::max<size_t>(1, R)));
+    if (ctx->flat_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
     CU(ctx, cudaMalloc((void **)&s.d_defer, sizeof(uint32_t) * std::max<size_t>(1, R)));
     if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
     mmc_batch_t &b = s.pub;
@@ -234,12 +242,21 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const uint32_t n = s.n_reads_submitted;
     // reset the slot's device state: err = ~0, view_n = 0, work counters and deferred count = 0
-    s.h_state[0] = ~0ull; s.h_state[1] = 0; s.h_state[2] = 0; s.h_state[3] = 0;
-    CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 32, cudaMemcpyHostToDevice, s.stream));
+    // layout: u64 [0] err, [1] view_n, [4] pool cursor; u32 [4] work counter of k_decode_warp, [5] reads it defers,
+    // [6] work counter of k_decode, [7] reads the flat path defers, [10] tiles, [11] reads with '.' blocks
+    memset(s.h_state, 0, 64);
+    s.h_state[0] = ~0ull;
+    CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 64, cudaMemcpyHostToDevice, s.stream));
     if (n == 0) { s.in_flight = true; s.timed = false; return MMC_OK; }
 
     uint32_t max_cig = 0, max_l = 0;
-    for (uint32_t i = 0; i < n; ++i) { max_cig = std::max(max_cig, b.n_cigar[i]); max_l = std::max(max_l, b.l_seq[i]); }
+    uint64_t pool_need = 0;                    // flat path: words of scratch if every read had two base classes and two '.' blocks
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
+        max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
+        const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
+        pool_need += 164 + 2ull * nc + 2 * (n_u4 + 2 + (L >> 6) + 2) + 2 * (n_u4 + 1) + 8;
+    }
     unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     if (grid == 0) grid = 1;
     uint32_t cig_words = max_cig > (uint32_t)ctx->cig_smem_cap ? (uint32_t)align_up(max_cig, 32) : 0;
@@ -282,7 +299,47 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     P.work_counter = st32 + 4;
     P.cig_smem_cap = ctx->cig_smem_cap; P.bitmap_smem_words = ctx->bitmap_smem_words; P.idx_smem_cap = ctx->idx_smem_cap;
 
+    FlatParams F;
+    memset(&F, 0, sizeof(F));
+    unsigned tgrid = 1;
+    if (ctx->flat_path) {
+        const size_t tile_need = (size_t)(b.mm_used / (kWChunks * 16)) + 2 * (size_t)kWBlocks * n + 64;
+        if (pool_need > s.pool_words || tile_need > s.tile_cap) {
+            CU(ctx, cudaStreamSynchronize(s.stream));
+            if (pool_need > s.pool_words) {
+                if (s.d_pool) CU(ctx, cudaFree(s.d_pool));
+                s.d_pool = nullptr; s.pool_words = 0;
+                CU(ctx, cudaMalloc((void **)&s.d_pool, pool_need * 4));
+                s.pool_words = pool_need;
+            }
+            if (tile_need > s.tile_cap) {
+                if (s.d_tiles) CU(ctx, cudaFree(s.d_tiles));
+                s.d_tiles = nullptr; s.tile_cap = 0;
+                CU(ctx, cudaMalloc((void **)&s.d_tiles, tile_need * sizeof(FlatTile)));
+                s.tile_cap = tile_need;
+            }
+        }
+        F.reads = s.d_reads;
+        F.fa.pool = s.d_pool; F.fa.cursor = s.d_state + 4; F.fa.cap = s.pool_words;
+        F.tiles = s.d_tiles; F.tile_cap = (uint32_t)std::min<size_t>(s.tile_cap, 0xffffffffu); F.n_tiles = st32 + 10; F.n_dot = st32 + 11;
+        F.defer_list = s.d_defer_flat; F.defer_n = st32 + 7;
+        tgrid = (unsigned)std::min<uint64_t>((tile_need + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 8);
+    }
+
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    if (ctx->flat_path) {
+        const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
+        const unsigned sgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads - 1) / kFThreads, (uint64_t)ctx->sm_count * 8);
+        MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
+        MMC_LAUNCH(k_flat_index, rgrid, (unsigned)kFThreads, s.stream, P, F);
+        MMC_LAUNCH(k_flat_tile_sums, tgrid, (unsigned)kFThreads, s.stream, P, F);
+        MMC_LAUNCH(k_flat_scan, sgrid, (unsigned)kFThreads, s.stream, P, F);
+        MMC_LAUNCH(k_flat_tile_calls, tgrid, (unsigned)kFThreads, s.stream, P, F);
+        MMC_LAUNCH(k_flat_finish, rgrid, (unsigned)kFThreads, s.stream, P, F);
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 6;
+        P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7;          // what is left goes through k_decode_warp
+    }
     if (ctx->warp_path) {
         // fast path: one warp per read; reads that do not fit a warp's shared-memory arena go to the list
         WarpParams W;
@@ -321,7 +378,8 @@ int wait_slot(mmc_ctx *ctx, Slot &s) {
     if (s.timed) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) ctx->tm.decode_ms += ms;
-        ctx->tm.deferred_reads += ((const uint32_t *)s.h_state)[5];
+        ctx->tm.deferred_reads += ((const uint32_t *)s.h_state)[5] + (ctx->warp_path ? 0 : ((const uint32_t *)s.h_state)[7]);
+        ctx->tm.flat_deferred_reads += ((const uint32_t *)s.h_state)[7];
         s.timed = false;
     }
     if (s.n_reads_submitted && s.h_state[0] != ~0ull) {
@@ -373,7 +431,8 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
     }
     if (const char *e = getenv("MMC_DECODE_PATH")) {         // "general": CTA-per-read kernel only (test hook / A-B timing)
-        if (!strcmp(e, "general")) ctx->warp_path = 0;
+        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->flat_path = 0; }
+        else if (!strcmp(e, "warp")) ctx->flat_path = 0;
     }
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->w_minb = v; }   // tuning
     ctx->w_arena_bytes = ctx->w_minb == 2 ? 14208u : ctx->w_minb == 3 ? 9344u : 6912u;   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
@@ -506,6 +565,10 @@ void mmc_destroy(mmc_ctx *ctx) {
         if (s.h_state) cudaFreeHost(s.h_state);
         if (s.d_view) cudaFree(s.d_view);
         if (s.d_defer) cudaFree(s.d_defer);
+        if (s.d_defer_flat) cudaFree(s.d_defer_flat);
+        if (s.d_reads) cudaFree(s.d_reads);
+        if (s.d_pool) cudaFree(s.d_pool);
+        if (s.d_tiles) cudaFree(s.d_tiles);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.ev_h0) cudaEventDestroy(s.ev_h0);
         if (s.ev_h1) cudaEventDestroy(s.ev_h1);

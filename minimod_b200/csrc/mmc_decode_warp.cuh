@@ -56,6 +56,11 @@ struct WBlock {                              // see BlockDesc
     uint32_t hdr_end, end;
     uint8_t  cls, is_n, dot, K;
     uint32_t any_req;
+    // rank index of the block's base class (w_build_index) and explicit-rank bitmap ('.' blocks): word offsets into flex
+    uint32_t o_idx, o_rd, rshift, cnt_cls, o_bm;
+    // filled once the block's skip counts are known
+    uint32_t n_calls, last1, ml_base;        // tokens, last rank + 1 (0 if none), first ML index (src/mod.c:1200)
+    uint32_t tile0, n_tiles;                 // flat path: the block's text tiles
     WCode    code[kMaxCodes];
 };
 
@@ -64,30 +69,45 @@ struct WState {                              // warp-uniform state of the read b
     const uint8_t  *seq, *mm, *ml;
     const uint32_t *ref2, *excm;
     unsigned long long *cells;
+    uint32_t *flex;                          // cq | cr | dir | idx | rd | bitmap words of this read
     uint32_t r, L, n_cig, mm_len, ml_len, rev, hp, ref_len;
     int32_t  tid, pos;
-    uint32_t o_cq, o_cr, o_dir, o_idx, o_bm; // word offsets into the flexible part of the arena
-    uint32_t cshift, gshift, ishift, n_samp, n_ent, n_u4, total_q, cnt_cls, cur_cls;
-    uint32_t o_rd, n_rd, rshift;             // rank directory: rd[k >> rshift] = index entry holding class rank (k >> rshift) << rshift
-    uint32_t carry_sum, prev_last;           // carries between the text tiles of a block
+    uint32_t o_cq, o_cr, o_dir;              // word offsets into flex
+    uint32_t cshift, gshift, ishift, n_samp, n_ent, n_u4, n_rd, total_q;
+    uint32_t cur_cls, cur_blk;               // fused path: class / block whose index currently occupies the arena
+    uint32_t carry_sum, prev_last;           // fused path: carries between the text tiles of a block
     uint32_t err;
     uint32_t n_semi, n_blocks;
 };
 
-struct WFixed {                              // fixed part of a warp's arena
+struct WRead {                               // per read: shared memory (fused path) or global scratch (flat path)
     WState   st;
     uint32_t semi[kWBlocks + 4];
     WBlock   blk[kWBlocks];
-    uint4    text[32 + 1];                   // the tile's text, chunk i at text[i] (+ one spill-over chunk)
+};
+
+struct WTile {                               // per warp, shared memory: one text tile of a block
+    uint4    text[32 + 1];                   // chunk i at text[i] (+ one spill-over chunk)
     uint32_t em[32];                         // per chunk: terminator mask (',' or block end) of its 32 following bytes
-    uint32_t rank[kWTokCap];                 // per token of the tile: byte offset in text -> base rank -> read position q
-    int32_t  refp[kWTokCap];                 // per call of the tile: reference position (aln[q]) or -1
+    uint32_t rank[kWTokCap];                 // per token: byte offset in text -> base rank -> read position q
+    int32_t  refp[kWTokCap];                 // per call: reference position (aln[q]) or -1
+};
+
+struct WFixed {                              // fixed part of a warp's arena on the fused path
+    WRead rd;
+    WTile tl;
 };
 
 struct WarpParams {
     uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(WFixed) + 256
     uint32_t *defer_list;                    // reads left to k_decode
     uint32_t *defer_n;
+};
+
+struct FlatAlloc {                           // flat path: bump allocator over a global scratch pool (words)
+    uint32_t *pool;
+    unsigned long long *cursor;
+    unsigned long long cap;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -154,10 +174,10 @@ __device__ __forceinline__ uint32_t count_u4_tail(uint4 v, uint32_t pat, uint32_
 }
 __device__ __forceinline__ uint4 ld16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
-__device__ __forceinline__ void w_raise(WFixed *wf, uint32_t code) { atomicCAS(&wf->st.err, 0u, code); }
-__device__ __forceinline__ uint32_t w_err(WFixed *wf) {
+__device__ __forceinline__ void w_raise(WRead *R, uint32_t code) { atomicCAS(&R->st.err, 0u, code); }
+__device__ __forceinline__ uint32_t w_err(WRead *R) {
     __syncwarp();
-    uint32_t e = *reinterpret_cast<volatile uint32_t *>(&wf->st.err);
+    uint32_t e = *reinterpret_cast<volatile uint32_t *>(&R->st.err);
     __syncwarp();
     return e;
 }
@@ -167,10 +187,11 @@ __device__ __forceinline__ uint32_t w_err(WFixed *wf) {
 // cq[s] = (read bases consumed before op s<<cshift) << 4 | that op's type; cr[s] = reference
 // bases consumed before it.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, const uint32_t *flex, uint32_t q) {
+__device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, uint32_t q) {
     AlnHit h; h.aln = -1; h.ins = -1; h.insoff = 0;
     const uint32_t total_q = S.total_q;
     if (q >= total_q) return h;
+    const uint32_t *flex = S.flex;
     const uint32_t *dir = flex + S.o_dir, *cq = flex + S.o_cq;
     const uint32_t g = S.gshift, b = q >> g;
     uint32_t lo = dir[b];
@@ -203,14 +224,15 @@ __device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------
-// bases_pos[cls][k] (src/mod.c:977-981): BAM position of the k-th base of the indexed class
-// ---------------------------------------------------------------------------------------
+// bases_pos[cls][k] (src/mod.c:977-981): BAM position of the k-th base of the block's class.
 // probe: index entry + vector that hold class rank k; rem = rank of k inside the vector
+// ---------------------------------------------------------------------------------------
 struct SelProbe { uint32_t u, rem; uint4 v; };
 template <bool C0>
-__device__ __forceinline__ SelProbe w_select_probe(const WState &S, const uint32_t *flex, uint32_t pat, uint32_t k) {
-    const uint32_t *idx = flex + S.o_idx;
-    uint32_t e = flex[S.o_rd + (k >> S.rshift)];                 // entry of rank (k >> rshift) << rshift: at or before k's
+__device__ __forceinline__ SelProbe w_select_probe(const WState &S, const WBlock *bd, uint32_t pat, uint32_t k) {
+    const uint32_t *flex = S.flex;
+    const uint32_t *idx = flex + bd->o_idx;
+    uint32_t e = flex[bd->o_rd + (k >> bd->rshift)];             // entry of rank (k >> rshift) << rshift: at or before k's
     uint32_t nxt = idx[e + 1u];
     while (nxt <= k) { ++e; nxt = idx[e + 1u]; }                 // few steps: 2^rshift ranks span few entries
     SelProbe p;
@@ -318,9 +340,10 @@ __device__ __noinline__ void w_emit_view(const DecodeParams &P, uint32_t r, int3
 
 // Everything after "base q of the read is a call and maps to ref_pos" (SURVEY.md A.5-A.8); see process_call().
 //   rd_code  2-bit code of the read base when the block's class pins it (C,G,T), else 4
-__device__ __forceinline__ void w_call_at(const DecodeParams &P, const WState &S, WFixed *wf, const uint8_t *s_lut,
+__device__ __forceinline__ void w_call_at(const DecodeParams &P, WRead *R, const uint8_t *s_lut,
                                           const WBlock *bd, uint32_t blk_ord, uint32_t q, int32_t ref_pos, uint32_t ins_off,
                                           bool implicit, uint32_t cidx, uint32_t ml_base, uint32_t rd_code) {
+    const WState &S = R->st;
     const uint32_t K = bd->K, is_n = bd->is_n;
     for (uint32_t m = 0; m < K; ++m) {
         const WCode cd = bd->code[m];
@@ -347,7 +370,7 @@ __device__ __forceinline__ void w_call_at(const DecodeParams &P, const WState &S
                 }
             }
         }
-        if (prob > 0xffu) { w_raise(wf, kErrMLIndex); return; }   // src/mod.c:1174
+        if (prob > 0xffu) { w_raise(R, kErrMLIndex); return; }    // src/mod.c:1174
         if (P.subtool == 1) {                                     // FREQ
             if (!implicit) {
                 const uint32_t f = cd.ri < kWLutSlots ? s_lut[cd.ri * 256 + prob] : P.req[cd.ri].lut[prob];   // src/mod.c:1181-1191
@@ -366,17 +389,18 @@ __device__ __forceinline__ void w_call_at(const DecodeParams &P, const WState &S
 }
 
 // "base q of the read is a call" (SURVEY.md A.4): read position -> reference position, then the above
-__device__ __forceinline__ void w_call(const DecodeParams &P, const WState &S, WFixed *wf, const uint32_t *flex, const uint8_t *s_lut,
+__device__ __forceinline__ void w_call(const DecodeParams &P, WRead *R, const uint8_t *s_lut,
                                        const WBlock *bd, uint32_t blk_ord, uint32_t q, bool implicit, uint32_t cidx,
                                        uint32_t ml_base, uint32_t rd_code) {
-    AlnHit h = w_cigar_lookup(S, flex, q);
+    const WState &S = R->st;
+    AlnHit h = w_cigar_lookup(S, q);
     int32_t ref_pos = h.aln;
     if (P.insertions && ref_pos < 0) {
-        if (implicit && S.rev) ref_pos = w_cigar_lookup(S, flex, S.L - 1u - q).ins;    // Q9 (src/mod.c:1234,1314)
+        if (implicit && S.rev) ref_pos = w_cigar_lookup(S, S.L - 1u - q).ins;          // Q9 (src/mod.c:1234,1314)
         else ref_pos = h.ins;
     }
     if (ref_pos < 0) return;                                      // src/mod.c:1127,1237,1317
-    w_call_at(P, S, wf, s_lut, bd, blk_ord, q, ref_pos, P.insertions ? h.insoff : 0u, implicit, cidx, ml_base, rd_code);
+    w_call_at(P, R, s_lut, bd, blk_ord, q, ref_pos, P.insertions ? h.insoff : 0u, implicit, cidx, ml_base, rd_code);
 }
 
 // commas (or any byte c) of 16 text bytes as a 16-bit mask (bit i <-> byte i)
@@ -387,21 +411,22 @@ __device__ __forceinline__ uint32_t byte_mask16(uint4 v, uint32_t c) {
     return a | (b << 4) | (d << 8) | (e << 12);
 }
 
-__device__ __forceinline__ void w_defer(const WarpParams &W, uint32_t r, uint32_t lane) {
-    if (lane == 0) W.defer_list[atomicAdd(W.defer_n, 1u)] = r;
+__device__ __forceinline__ void w_defer(uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane) {
+    if (lane == 0) defer_list[atomicAdd(defer_n, 1u)] = r;
 }
 __device__ __forceinline__ void w_report(const DecodeParams &P, uint32_t r, uint32_t code, uint32_t lane) {
     if (lane == 0) atomicMin(P.err, ((unsigned long long)r << 32) | code);
 }
 
 // one MM block header (src/mod.c:1003-1062); same rules as k_decode's (2b).  Returns an error code.
-__device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, WFixed *wf, uint32_t blk) {
-    const WState &S = wf->st;
-    WBlock &bd = wf->blk[blk];
-    const uint32_t start = blk == 0 ? 0u : wf->semi[blk - 1u] + 1u;
-    const uint32_t end = blk < S.n_semi ? wf->semi[blk] : S.mm_len;
+__device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, WRead *R, uint32_t blk) {
+    const WState &S = R->st;
+    WBlock &bd = R->blk[blk];
+    const uint32_t start = blk == 0 ? 0u : R->semi[blk - 1u] + 1u;
+    const uint32_t end = blk < S.n_semi ? R->semi[blk] : S.mm_len;
     const uint8_t *mm = S.mm;
     bd.end = end; bd.hdr_end = end; bd.K = 0; bd.any_req = 0; bd.cls = 0; bd.is_n = 0; bd.dot = 1;
+    bd.o_idx = 0; bd.o_rd = 0; bd.rshift = 0; bd.cnt_cls = 0; bd.o_bm = 0; bd.n_calls = 0; bd.last1 = 0; bd.ml_base = 0; bd.tile0 = 0; bd.n_tiles = 0;
     for (int k = 0; k < kMaxCodes; ++k) { WCode c; c.ri = -1; c.outc = 0; c.ctx_mode = kCtxNone; c.ctx_len = 0; c.pat2 = 0; bd.code[k] = c; }
     uint32_t i = start;
     const uint32_t base_c = i < end ? mm[i] : 0u;
@@ -465,18 +490,26 @@ __device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, WFixed *w
     return kErrNone;
 }
 
+// does block b need the rank index of its class / an explicit-rank bitmap?
+__device__ __forceinline__ bool w_needs_index(const WBlock *bd) { return bd->any_req && (!bd->is_n || bd->dot); }
+__device__ __forceinline__ bool w_needs_bitmap(const WBlock *bd) { return bd->any_req && bd->dot; }
+
 // ---------------------------------------------------------------------------------------
-// phase 1 (per read): batch record -> WState, MM block table, arena layout, CIGAR prefix sums.
-// Returns false when the read is finished already (deferred to k_decode, or fatal and reported).
+// phase 1 (per read): batch record -> WState, MM block table, scratch layout, CIGAR prefix sums.
+// Returns false when the read is finished already (deferred to the next kernel, or fatal and reported).
+//   fused path: fa == nullptr, the scratch is the warp's arena `flex` of flex_words words; one rank index
+//               and one bitmap are shared by all blocks (rebuilt when the class changes)
+//   flat path:  the scratch comes from the global pool `fa`; one index per distinct class and one
+//               bitmap per '.' block, so that later kernels can work on any block / tile independently
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ bool w_setup_read(const DecodeParams &P, const WarpParams &W, WFixed *wf, uint32_t *flex,
-                                          uint32_t flex_words, uint32_t r, uint32_t lane) {
-    WState &S = wf->st;
+__device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint32_t *flex, uint32_t flex_words, const FlatAlloc *fa,
+                                          uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane) {
+    WState &S = R->st;
     const int32_t tid = P.tid[r];
     const uint32_t L = P.l_seq[r], n_cig = P.n_cigar[r], mm_len = P.mm_len[r];
     const uint8_t *mm = P.mm + P.mm_off[r];
     if (tid < 0 || tid >= P.n_contigs || P.contigs[tid].ref2 == nullptr) { w_report(P, r, kErrNoContig, lane); return false; }
-    if (L >= kWMaxL) { w_defer(W, r, lane); return false; }
+    if (L >= kWMaxL) { w_defer(defer_list, defer_n, r, lane); return false; }
     const uint32_t *cig = P.cigar + P.cigar_off[r];
     const int32_t pos = P.pos[r];
     const uint32_t ref_len = P.contigs[tid].len;
@@ -486,7 +519,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, const WarpParam
         S.ref2 = cd.ref2; S.excm = cd.excm; S.cells = cd.cells; S.ref_len = cd.len;
         S.r = r; S.L = L; S.n_cig = n_cig; S.mm_len = mm_len; S.ml_len = P.ml_len[r];
         S.rev = (P.flag[r] >> 4) & 1u; S.hp = P.hp[r]; S.tid = tid; S.pos = pos;
-        S.err = 0; S.cur_cls = 0xffu; S.cnt_cls = 0;
+        S.err = 0; S.cur_cls = 0xffu; S.cur_blk = 0; S.n_blocks = 0;
     }
 
     // ---- MM blocks: positions of ';'
@@ -505,49 +538,83 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, const WarpParam
         while (mask) {
             const uint32_t bit = (uint32_t)__ffs((int)mask) - 1u;
             mask &= mask - 1u;
-            if (ord < (uint32_t)kWBlocks) wf->semi[ord] = p0 + bit;
+            if (ord < (uint32_t)kWBlocks) R->semi[ord] = p0 + bit;
             ++ord;
         }
         n_semi += __shfl_sync(kFull, incl, 31);
     }
     uint32_t n_blocks = n_semi;
     if (mm_len > 0 && mm[mm_len - 1u] != ';') n_blocks += 1;                        // unterminated last block
-    if (n_blocks > (uint32_t)kWBlocks) { w_defer(W, r, lane); return false; }
+    if (n_blocks > (uint32_t)kWBlocks) { w_defer(defer_list, defer_n, r, lane); return false; }
     if (lane == 0) { S.n_semi = n_semi; S.n_blocks = n_blocks; }
     __syncwarp();
 
     // ---- block headers, one lane each
-    uint32_t herr = kErrNone, my_dot_work = 0;
+    uint32_t herr = kErrNone, my_idx = 0, my_bm = 0, my_cls = 0;
     if (lane < n_blocks) {
-        herr = w_parse_header(P, wf, lane);
-        my_dot_work = herr == kErrNone && wf->blk[lane].any_req && wf->blk[lane].dot;
+        herr = w_parse_header(P, R, lane);
+        if (herr == kErrNone) { my_idx = w_needs_index(&R->blk[lane]); my_bm = w_needs_bitmap(&R->blk[lane]); my_cls = R->blk[lane].cls; }
     }
     const uint32_t herr_mask = __ballot_sync(kFull, herr != kErrNone);
     if (herr_mask) herr = __shfl_sync(kFull, herr, __ffs((int)herr_mask) - 1);
-    const bool need_bm_any = __ballot_sync(kFull, my_dot_work != 0u) != 0u;
+    const uint32_t idx_mask = __ballot_sync(kFull, my_idx != 0u), bm_mask = __ballot_sync(kFull, my_bm != 0u);
+    uint32_t cls_set = 0;                                                            // classes that need an index
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        const uint32_t c = __shfl_sync(kFull, my_cls, (int)b);
+        if ((idx_mask >> b) & 1u) cls_set |= 1u << c;
+    }
 
-    // ---- arena layout
+    // ---- scratch layout
     const uint32_t n_u4 = (L + 31u) >> 5;
     uint32_t gshift = 8;
     while (((L >> gshift) + 2u) > 160u) ++gshift;
     const uint32_t n_dir = (L >> gshift) + 2u;
     const uint32_t n_rd = (L >> 6) + 2u;
-    const uint32_t bm_words = need_bm_any ? ((L + 31u) >> 5) + 1u : 0u;
-    uint32_t cshift = 0, ishift = 0, n_samp, n_ent;
+    const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
+    const uint32_t n_idx = fa ? (uint32_t)__popc(cls_set) : (idx_mask ? 1u : 0u);
+    const uint32_t n_bm = fa ? (uint32_t)__popc(bm_mask) : (bm_mask ? 1u : 0u);
+    const uint32_t cap = fa ? (1u << 20) : flex_words;                               // flat: sample only absurdly large reads
+    uint32_t cshift = 0, ishift = 0, n_samp, n_ent, need;
     for (;;) {
         n_samp = (n_cig + (1u << cshift) - 1u) >> cshift;
         if (n_samp == 0u) n_samp = 1u;
         n_ent = (n_u4 + (1u << ishift) - 1u) >> ishift;
-        const uint32_t need = n_dir + n_rd + bm_words + 2u * n_samp + n_ent + 2u;
-        if (need <= flex_words) break;
-        if (cshift >= (uint32_t)kWMaxCShift && ishift >= (uint32_t)kWMaxIShift) { w_defer(W, r, lane); return false; }
+        need = n_dir + 2u * n_samp + n_idx * (n_ent + 2u + n_rd) + n_bm * bm_words;
+        if (need <= cap) break;
+        if (cshift >= (uint32_t)kWMaxCShift && ishift >= (uint32_t)kWMaxIShift) { w_defer(defer_list, defer_n, r, lane); return false; }
         if ((2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
         else ++ishift;
     }
-    const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_idx = o_cr + n_samp, o_rd = o_idx + n_ent + 2u, o_bm = o_rd + n_rd;
+    if (fa) {                                                                        // bump-allocate from the global pool
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(fa->cursor, (unsigned long long)((need + 3u) & ~3u));
+        base = ((unsigned long long)__shfl_sync(kFull, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)base, 0);
+        if (base + need > fa->cap) { w_defer(defer_list, defer_n, r, lane); return false; }
+        flex = fa->pool + base;
+    }
+    const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = o_cr + n_samp;
     if (lane == 0) {
-        S.o_dir = o_dir; S.o_cq = o_cq; S.o_cr = o_cr; S.o_idx = o_idx; S.o_rd = o_rd; S.n_rd = n_rd; S.o_bm = o_bm;
-        S.cshift = cshift; S.gshift = gshift; S.ishift = ishift; S.n_samp = n_samp; S.n_ent = n_ent; S.n_u4 = n_u4;
+        S.flex = flex;
+        S.o_dir = o_dir; S.o_cq = o_cq; S.o_cr = o_cr;
+        S.cshift = cshift; S.gshift = gshift; S.ishift = ishift; S.n_samp = n_samp; S.n_ent = n_ent; S.n_u4 = n_u4; S.n_rd = n_rd;
+        // per block: where its class index / bitmap live
+        uint32_t cls_off[5] = {0, 0, 0, 0, 0}, next = o_var, seen = 0;
+        for (uint32_t b = 0; b < n_blocks; ++b) {
+            WBlock &bd = R->blk[b];
+            if ((idx_mask >> b) & 1u) {
+                const uint32_t c = bd.cls;
+                if (!fa) { bd.o_idx = o_var; bd.o_rd = o_var + n_ent + 2u; }
+                else {
+                    if (!((seen >> c) & 1u)) { cls_off[c] = next; next += n_ent + 2u + n_rd; seen |= 1u << c; }
+                    bd.o_idx = cls_off[c]; bd.o_rd = cls_off[c] + n_ent + 2u;
+                }
+            }
+        }
+        if (!fa) next = o_var + n_idx * (n_ent + 2u + n_rd);
+        for (uint32_t b = 0; b < n_blocks; ++b) {
+            WBlock &bd = R->blk[b];
+            if ((bm_mask >> b) & 1u) { bd.o_bm = next; if (fa) next += bm_words; }
+        }
     }
 
     // ---- CIGAR prefix sums == get_aln() (src/mod.c:811-880)
@@ -563,17 +630,17 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, const WarpParam
             if (op == 0u || op == 7u || op == 8u) { ql = len; rl = len; }
             else if (op == 1u || op == 4u) ql = len;
             else if (op == 2u || op == 3u) rl = len;
-            else if (op == 5u) w_raise(wf, kErrHardClip);
-            else w_raise(wf, kErrCigarOp);
+            else if (op == 5u) w_raise(R, kErrHardClip);
+            else w_raise(R, kErrCigarOp);
         }
         const uint32_t iq = warp_incl_scan_sat(ql, lane), ir = warp_incl_scan_sat(rl, lane);
         if (i < n_cig) {
             const uint32_t q0 = sat_add(carry_q, iq >= kSat ? kSat : iq - ql), r0 = sat_add(carry_r, ir >= kSat ? kSat : ir - rl);
             const bool alnop = op == 0u || op == 7u || op == 8u;
-            if ((alnop || (op == 1u && P.insertions)) && len > 0 && sat_add(q0, ql) > L) w_raise(wf, kErrCigarLen);
+            if ((alnop || (op == 1u && P.insertions)) && len > 0 && sat_add(q0, ql) > L) w_raise(R, kErrCigarLen);
             if (alnop && len > 0) {
                 const long long last = (long long)pos + r0 + len - 1;
-                if (pos < 0 || last >= (long long)ref_len) w_raise(wf, kErrRefRange);
+                if (pos < 0 || last >= (long long)ref_len) w_raise(R, kErrRefRange);
             }
             if ((i & cmask) == 0u) { flex[o_cq + (i >> cshift)] = ((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op; flex[o_cr + (i >> cshift)] = r0; }
             if (ql > 0u && q0 < L) {                              // directory: sample that holds each bucket's first base
@@ -585,9 +652,9 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, const WarpParam
         carry_r = sat_add(carry_r, __shfl_sync(kFull, ir, 31));
     }
     if (lane == 0) S.total_q = carry_q < L ? carry_q : L;
-    uint32_t err = w_err(wf);
+    uint32_t err = w_err(R);
     if (!err) err = herr;
-    if (err) { w_report(P, r, err, lane); return false; }
+    if (err) { if (lane == 0) S.n_blocks = 0; w_report(P, r, err, lane); return false; }
     if (lane == 0) {
         const int32_t lo = pos > 0 ? pos - 1 : 0;
         long long hi = (long long)pos + carry_r + 1;
@@ -630,10 +697,12 @@ __device__ __forceinline__ void w_count_entries(const WState &S, uint32_t *idx, 
     }
 }
 
-__device__ __noinline__ void w_build_index(WFixed *wf, uint32_t *flex, uint32_t cls, uint32_t lane) {
-    WState &S = wf->st;
-    uint32_t *idx = flex + S.o_idx, *rd = flex + S.o_rd;
-    const uint32_t n_ent = S.n_ent, pat = class_pat(cls);
+// builds the index of block jb's class at (bd->o_idx, bd->o_rd) and fills bd->cnt_cls / bd->rshift
+__device__ __noinline__ void w_build_index(WRead *R, uint32_t jb, uint32_t lane) {
+    WState &S = R->st;
+    WBlock *bd = &R->blk[jb];
+    uint32_t *idx = S.flex + bd->o_idx, *rd = S.flex + bd->o_rd;
+    const uint32_t cls = bd->cls, n_ent = S.n_ent, pat = class_pat(cls);
     __syncwarp();
     if (cls == 0u) w_count_entries<true>(S, idx, pat, lane); else w_count_entries<false>(S, idx, pat, lane);
     __syncwarp();
@@ -649,7 +718,7 @@ __device__ __noinline__ void w_build_index(WFixed *wf, uint32_t *flex, uint32_t 
     for (uint32_t e = e0; e < e1; ++e) { const uint32_t c = idx[e]; idx[e] = run; run += c; }
     uint32_t rshift = 2;
     while (((total >> rshift) + 1u) > S.n_rd) ++rshift;
-    if (lane == 0) { idx[n_ent] = total; S.cur_cls = cls; S.cnt_cls = total; S.rshift = rshift; }
+    if (lane == 0) { idx[n_ent] = total; bd->cnt_cls = total; bd->rshift = rshift; }
     __syncwarp();
     // rank directory: each multiple of 2^rshift below `total` lies in exactly one entry's rank range
     for (uint32_t e = lane; e < n_ent; e += 32u) {
@@ -673,20 +742,23 @@ __device__ __noinline__ uint32_t w_parse_long(const uint8_t *tx, uint32_t nd, ui
 // ---------------------------------------------------------------------------------------
 // phase 3 (per text tile of a block): skip counts -> base ranks (src/mod.c:1066-1098).
 // The tile is 31 chunks of 16 bytes starting at tb (lane 31 holds look-ahead text only).
-// Leaves the ranks of the tile's tokens in wf->rank[0..n) and returns n.
+// Leaves carry_in + (prefix sum of skip+1) - 1 of the tile's tokens in T->rank[0..n), returns n
+// and the saturating sum of the tile's (skip+1) in *sum_out.
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t w_tile_ranks(WFixed *wf, uint32_t tb, uint32_t a0, uint32_t a1, uint32_t lane) {
-    WState &S = wf->st;
+__device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb, uint32_t a0, uint32_t a1, uint32_t carry_in,
+                                                 uint32_t *sum_out, uint32_t lane) {
+    const WState &S = R->st;
     const uint32_t mm_len = S.mm_len;
+    const uint8_t *mm = S.mm;
     const uint32_t p0 = tb + lane * 16u;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (p0 < mm_len) v = ld16(S.mm + p0);
-    wf->text[lane] = v;
+    if (p0 < mm_len) v = ld16(mm + p0);
+    T->text[lane] = v;
     const uint32_t cm = byte_mask16(v, ',');
     const uint32_t up = __shfl_up_sync(kFull, cm, 1);
     const uint32_t ncm = __shfl_down_sync(kFull, cm, 1);
-    const uint32_t pbit = lane == 0 ? S.prev_last : (up >> 15) & 1u;
-    const uint32_t next_prev_last = (__shfl_sync(kFull, cm, kWChunks - 1) >> 15) & 1u;
+    uint32_t pbit = (up >> 15) & 1u;
+    if (lane == 0) pbit = (tb > a0 && mm[tb - 1u] == ',') ? 1u : 0u;
     uint32_t st = ((cm << 1) | pbit) & ~cm & 0xffffu;              // token starts: previous byte is ','
     // clip to [a0, a1) and force a start at a0 (src/mod.c:1066: the list begins right after the header)
     uint32_t lo_b = a0 > p0 ? a0 - p0 : 0u, hi_b = a1 > p0 ? a1 - p0 : 0u;
@@ -698,25 +770,25 @@ __device__ __noinline__ uint32_t w_tile_ranks(WFixed *wf, uint32_t tb, uint32_t 
     if (lane >= (uint32_t)kWChunks) st = 0;
     uint32_t em = cm | (ncm << 16);                               // token terminators: ',' or the block end
     if (a1 >= p0 && a1 - p0 < 32u) em |= 1u << (a1 - p0);
-    wf->em[lane] = em;
+    T->em[lane] = em;
     const uint32_t n_tok = (uint32_t)__popc(st);
     const uint32_t incl = warp_incl_scan(n_tok, lane);
     const uint32_t tile_cnt = __shfl_sync(kFull, incl, 31);
     uint32_t slot = incl - n_tok;
     const uint32_t base_off = lane * 16u;
     while (st) {                                                  // byte offset of every token of this chunk
-        wf->rank[slot++] = base_off + (uint32_t)__ffs((int)st) - 1u;
+        T->rank[slot++] = base_off + (uint32_t)__ffs((int)st) - 1u;
         st &= st - 1u;
     }
     __syncwarp();
-    const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(wf->text);
-    uint32_t carry = S.carry_sum;
+    const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(T->text);
+    uint32_t carry = carry_in, total = 0;
     for (uint32_t c0 = 0; c0 < tile_cnt; c0 += 32u) {
         const uint32_t c = c0 + lane;
         uint32_t x = 0;
         if (c < tile_cnt) {                                       // one token per lane: SWAR decimal parse
-            const uint32_t off = wf->rank[c];
-            const uint32_t rest = wf->em[off >> 4] >> ((off & 15u) + 1u);
+            const uint32_t off = T->rank[c];
+            const uint32_t rest = T->em[off >> 4] >> ((off & 15u) + 1u);
             uint32_t nd = rest ? (uint32_t)__ffs((int)rest) : 32u, val = 0, bad = 0;
             if (nd > 9u) { bad = 1; nd = 0; }                     // src/mod.c:1080-1085
             if (nd <= 4u) {
@@ -729,22 +801,23 @@ __device__ __noinline__ uint32_t w_tile_ranks(WFixed *wf, uint32_t tb, uint32_t 
                 const uint32_t pr = (dg * 10u + (dg >> 8)) & 0x00ff00ffu;              // (10*b0+b1) | (10*b2+b3) << 16
                 val = (pr & 0xffffu) * 100u + (pr >> 16);
             } else {
-                val = w_parse_long(reinterpret_cast<const uint8_t *>(wf->text) + off, nd, &bad);
+                val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
             }
-            if (bad) { w_raise(wf, kErrMMSkip); val = 0; }
+            if (bad) { w_raise(R, kErrMMSkip); val = 0; }
             x = val + 1u;
         }
         const uint32_t si = warp_incl_scan_sat(x, lane);
-        if (c < tile_cnt) wf->rank[c] = sat_add(carry, si) - 1u;  // base_rank (src/mod.c:1098)
-        carry = sat_add(carry, __shfl_sync(kFull, si, 31));
+        if (c < tile_cnt) T->rank[c] = sat_add(carry, si) - 1u;   // base_rank (src/mod.c:1098)
+        const uint32_t rt = __shfl_sync(kFull, si, 31);
+        carry = sat_add(carry, rt); total = sat_add(total, rt);
     }
-    if (lane == 0) { S.carry_sum = carry; S.prev_last = next_prev_last; }
+    *sum_out = total;
     __syncwarp();
     return tile_cnt;
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 4 (per text tile): the explicit calls whose ranks are in wf->rank[0..n).  Three passes
+// phase 4 (per text tile): the explicit calls whose ranks are in T->rank[0..n).  Three passes
 // staged through shared memory so that each is a short loop with independent iterations:
 //   select  base rank -> read position q            (bases_pos[][], src/mod.c:1102-1113)
 //   map     q -> reference position                 (aln[], src/mod.c:1122)
@@ -753,80 +826,70 @@ __device__ __noinline__ uint32_t w_tile_ranks(WFixed *wf, uint32_t tb, uint32_t 
 constexpr uint32_t kNoCall = 0xffffffffu;
 
 template <bool C0>
-__device__ __forceinline__ void w_pass_select(WFixed *wf, uint32_t *flex, uint32_t pat, uint32_t n, uint32_t need_bm, uint32_t lane) {
-    const WState &S = wf->st;
-    const uint32_t rev = S.rev, cnt_cls = S.cnt_cls;
-    uint32_t *bm = flex + S.o_bm;
-    for (uint32_t c = lane; c < n; c += 64u) {                    // two calls per lane in flight
-        const uint32_t c1 = c + 32u;
-        const bool have1 = c1 < n;
-        const uint32_t r0 = wf->rank[c], r1 = have1 ? wf->rank[c1] : 0u;
-        const bool ok0 = r0 < cnt_cls, ok1 = have1 && r1 < cnt_cls;
-        if (!ok0 || (have1 && !ok1)) w_raise(wf, kErrMMRank);     // src/mod.c:1116
-        SelProbe p0, p1;
-        if (ok0) p0 = w_select_probe<C0>(S, flex, pat, rev ? cnt_cls - 1u - r0 : r0);
-        if (ok1) p1 = w_select_probe<C0>(S, flex, pat, rev ? cnt_cls - 1u - r1 : r1);
-        if (need_bm) {
-            if (ok0) atomicOr(&bm[r0 >> 5], 1u << (r0 & 31u));
-            if (ok1) atomicOr(&bm[r1 >> 5], 1u << (r1 & 31u));
-        }
-        wf->rank[c] = ok0 ? w_select_resolve<C0>(p0, pat) : kNoCall;
-        if (have1) wf->rank[c1] = ok1 ? w_select_resolve<C0>(p1, pat) : kNoCall;
+__device__ __forceinline__ void w_pass_select(WRead *R, WTile *T, const WBlock *bd, uint32_t pat, uint32_t n, uint32_t need_bm, uint32_t lane) {
+    const WState &S = R->st;
+    const uint32_t rev = S.rev, cnt_cls = bd->cnt_cls;
+    uint32_t *bm = S.flex + bd->o_bm;
+    for (uint32_t c = lane; c < n; c += 32u) {
+        const uint32_t r0 = T->rank[c];
+        if (r0 >= cnt_cls) { w_raise(R, kErrMMRank); T->rank[c] = kNoCall; continue; }     // src/mod.c:1116
+        const SelProbe p0 = w_select_probe<C0>(S, bd, pat, rev ? cnt_cls - 1u - r0 : r0);
+        if (need_bm) atomicOr(&bm[r0 >> 5], 1u << (r0 & 31u));
+        T->rank[c] = w_select_resolve<C0>(p0, pat);
     }
 }
 
-__device__ __noinline__ void w_tile_calls(const DecodeParams &P, WFixed *wf, uint32_t *flex, const uint8_t *s_lut, uint32_t jb,
-                                          uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
-    const WState &S = wf->st;
-    const WBlock *bd = &wf->blk[jb];
+__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, uint32_t jb,
+                                             uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
+    const WState &S = R->st;
+    const WBlock *bd = &R->blk[jb];
     const uint32_t cls = bd->cls, need_bm = bd->dot;
     const uint32_t pat = class_pat(cls), rd_code = cls >= 1u && cls <= 3u ? cls : 4u;
     // ---- select
     if (bd->is_n) {                                               // src/mod.c:1102-1107
         const uint32_t L = S.L, rev = S.rev;
-        uint32_t *bm = flex + S.o_bm;
+        uint32_t *bm = S.flex + bd->o_bm;
         for (uint32_t c = lane; c < n; c += 32u) {
-            const uint32_t rank = wf->rank[c];
-            if (rank >= L) { w_raise(wf, kErrMMRank); wf->rank[c] = kNoCall; continue; }
+            const uint32_t rank = T->rank[c];
+            if (rank >= L) { w_raise(R, kErrMMRank); T->rank[c] = kNoCall; continue; }
             if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
-            wf->rank[c] = rev ? L - 1u - rank : rank;
+            T->rank[c] = rev ? L - 1u - rank : rank;
         }
-    } else if (cls == 0u) w_pass_select<true>(wf, flex, pat, n, need_bm, lane);
-    else w_pass_select<false>(wf, flex, pat, n, need_bm, lane);
+    } else if (cls == 0u) w_pass_select<true>(R, T, bd, pat, n, need_bm, lane);
+    else w_pass_select<false>(R, T, bd, pat, n, need_bm, lane);
     if (P.insertions) {                                           // ins[] fall-back and ins_offset: fused map + update
         for (uint32_t c = lane; c < n; c += 32u) {
-            const uint32_t q = wf->rank[c];
-            if (q != kNoCall) w_call(P, S, wf, flex, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
+            const uint32_t q = T->rank[c];
+            if (q != kNoCall) w_call(P, R, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
         }
         return;
     }
     // ---- map
     for (uint32_t c = lane; c < n; c += 32u) {
-        const uint32_t q = wf->rank[c];
-        wf->refp[c] = q != kNoCall ? w_cigar_lookup(S, flex, q).aln : -1;
+        const uint32_t q = T->rank[c];
+        T->refp[c] = q != kNoCall ? w_cigar_lookup(S, q).aln : -1;
     }
     // ---- update
     for (uint32_t c = lane; c < n; c += 32u) {
-        const int32_t ref_pos = wf->refp[c];
+        const int32_t ref_pos = T->refp[c];
         if (ref_pos < 0) continue;                                // src/mod.c:1127
-        w_call_at(P, S, wf, s_lut, bd, jb, wf->rank[c], ref_pos, 0u, false, cidx0 + c, ml_base, rd_code);
+        w_call_at(P, R, s_lut, bd, jb, T->rank[c], ref_pos, 0u, false, cidx0 + c, ml_base, rd_code);
     }
 }
 
 // implicit calls of a '.' block (src/mod.c:1203-1367): every base of the class whose rank is not
-// in the explicit-rank bitmap.  Cold for '?' data; all state comes from shared memory.
-__device__ __noinline__ void w_implicit_block(const DecodeParams &P, WFixed *wf, uint32_t *flex, const uint8_t *s_lut, uint32_t jb,
-                                              uint32_t carry_cnt, uint32_t ml_base, uint32_t lane) {
-    const WState &S = wf->st;
-    const WBlock *bd = &wf->blk[jb];
-    const uint32_t *bm = flex + S.o_bm, *idx = flex + S.o_idx;
-    const uint32_t cnt_cls = S.cnt_cls;
+// in the explicit-rank bitmap.  Needs bd->n_calls / last1 / ml_base.
+__device__ __forceinline__ void w_implicit_block(const DecodeParams &P, WRead *R, const uint8_t *s_lut, uint32_t jb, uint32_t lane) {
+    const WState &S = R->st;
+    const WBlock *bd = &R->blk[jb];
+    const uint32_t *bm = S.flex + bd->o_bm, *idx = S.flex + bd->o_idx;
+    const uint32_t cnt_cls = bd->cnt_cls, ml_base = bd->ml_base;
     if (bd->is_n) {
-        const uint32_t last1 = carry_cnt > 0 ? S.carry_sum : 0u;                    // last + 1
+        const uint32_t last1 = bd->n_calls > 0 ? bd->last1 : 0u;                    // last + 1
         const uint32_t bound = last1 > cnt_cls ? last1 : cnt_cls;                   // Q8
         for (uint32_t s = lane; s < bound; s += 32u) {
             if ((bm[s >> 5] >> (s & 31u)) & 1u) continue;
-            w_call(P, S, wf, flex, s_lut, bd, jb, S.rev ? S.L - 1u - s : s, true, s, ml_base, 4u);
+            w_call(P, R, s_lut, bd, jb, S.rev ? S.L - 1u - s : s, true, s, ml_base, 4u);
         }
         return;
     }
@@ -846,11 +909,35 @@ __device__ __noinline__ void w_implicit_block(const DecodeParams &P, WFixed *wf,
                     const uint32_t s = S.rev ? cnt_cls - 1u - fr : fr;
                     ++fr;
                     if ((bm[s >> 5] >> (s & 31u)) & 1u) continue;
-                    w_call(P, S, wf, flex, s_lut, bd, jb, b0 + t, true, s, ml_base, rd_code);
+                    w_call(P, R, s_lut, bd, jb, b0 + t, true, s, ml_base, rd_code);
                 }
             }
         }
     }
+}
+
+// call LUTs of the first kWLutSlots -c entries -> shared memory of the CTA (all threads call it)
+__device__ __forceinline__ void w_stage_luts(const DecodeParams &P, uint8_t *s_lut) {
+    const uint32_t n_lut = P.n_req < kWLutSlots ? (uint32_t)P.n_req : (uint32_t)kWLutSlots;
+    for (uint32_t i = threadIdx.x; i < n_lut * 256u; i += blockDim.x) s_lut[i] = P.req[i >> 8].lut[i & 255u];
+    __syncthreads();
+}
+
+// fused path: the non-inlined pieces of the block loop
+__device__ __noinline__ uint32_t w_fused_tile(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, uint32_t jb, uint32_t tb,
+                                              uint32_t carry_cnt, uint32_t ml_base, uint32_t lane) {
+    WState &S = R->st;
+    const WBlock *bd = &R->blk[jb];
+    uint32_t sum = 0;
+    const uint32_t n = w_tile_ranks(R, T, tb, bd->hdr_end, bd->end, S.carry_sum, &sum, lane);
+    if (bd->any_req && n) w_tile_calls(P, R, T, s_lut, jb, n, carry_cnt, ml_base, lane);
+    __syncwarp();
+    if (lane == 0) S.carry_sum = sat_add(S.carry_sum, sum);
+    __syncwarp();
+    return n;
+}
+__device__ __noinline__ void w_fused_implicit(const DecodeParams &P, WRead *R, const uint8_t *s_lut, uint32_t jb, uint32_t lane) {
+    w_implicit_block(P, R, s_lut, jb, lane);
 }
 
 // MINB = resident CTAs per SM the register allocation is bounded for (2: 128 regs, 3: 80, 4: 64);
@@ -858,51 +945,56 @@ __device__ __noinline__ void w_implicit_block(const DecodeParams &P, WFixed *wf,
 template <int MINB>
 __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_constant__ DecodeParams P, const __grid_constant__ WarpParams W) {
     MMC_DYN_SMEM(uint4, w_dyn);
-    // call LUTs of the first kWLutSlots -c entries, shared by the CTA
     uint8_t *s_lut = reinterpret_cast<uint8_t *>(w_dyn);
-    const uint32_t n_lut = P.n_req < kWLutSlots ? (uint32_t)P.n_req : (uint32_t)kWLutSlots;
-    for (uint32_t i = threadIdx.x; i < n_lut * 256u; i += blockDim.x) s_lut[i] = P.req[i >> 8].lut[i & 255u];
-    __syncthreads();
+    w_stage_luts(P, s_lut);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint8_t *arena = reinterpret_cast<uint8_t *>(w_dyn) + kWLutSlots * 256 + (size_t)warp * W.arena_bytes;
     WFixed *wf = reinterpret_cast<WFixed *>(arena);
+    WRead *R = &wf->rd;
+    WTile *T = &wf->tl;
     uint32_t *flex = reinterpret_cast<uint32_t *>(arena + sizeof(WFixed));
     const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
-    WState &S = wf->st;
+    WState &S = R->st;
     for (;;) {
         uint32_t r = 0;
-        if (lane == 0) r = atomicAdd(P.work_counter, 1u);
+        if (lane == 0) {
+            r = atomicAdd(P.work_counter, 1u);
+            if (P.read_list) r = r < *P.read_list_n ? P.read_list[r] : 0xffffffffu;     // reads deferred by the flat path
+        }
         r = __shfl_sync(kFull, r, 0);
         if (r >= P.n_reads) break;
         __syncwarp();
-        if (!w_setup_read(P, W, wf, flex, flex_words, r, lane)) continue;
+        if (!w_setup_read(P, R, flex, flex_words, nullptr, W.defer_list, W.defer_n, r, lane)) continue;
 
         // ---- blocks in order
         const uint32_t n_blocks = S.n_blocks;
         uint32_t ml_base = 0, err = 0;
         for (uint32_t jb = 0; jb < n_blocks; ++jb) {
-            const WBlock *bd = &wf->blk[jb];
+            WBlock *bd = &R->blk[jb];
             const uint32_t a0 = bd->hdr_end, a1 = bd->end, cls = bd->cls;      // cls is 4 when the canonical base is N
-            const bool work = bd->any_req != 0u, need_bm = work && bd->dot;
-            if (work && (!bd->is_n || bd->dot) && S.cur_cls != cls) w_build_index(wf, flex, cls, lane);
+            const bool need_bm = w_needs_bitmap(bd);
+            if (w_needs_index(bd)) {
+                if (S.cur_cls != cls) {
+                    w_build_index(R, jb, lane);
+                    if (lane == 0) { S.cur_cls = cls; S.cur_blk = jb; }
+                } else if (lane == 0) { bd->cnt_cls = R->blk[S.cur_blk].cnt_cls; bd->rshift = R->blk[S.cur_blk].rshift; }
+            }
             if (need_bm) {
                 const uint32_t words = ((S.L + 31u) >> 5) + 1u;
-                for (uint32_t w = lane; w < words; w += 32u) flex[S.o_bm + w] = 0;
+                for (uint32_t w = lane; w < words; w += 32u) flex[bd->o_bm + w] = 0;
             }
-            if (lane == 0) { S.carry_sum = 0; S.prev_last = 0; }
+            if (lane == 0) S.carry_sum = 0;
             __syncwarp();
             uint32_t carry_cnt = 0;
-            for (uint32_t tb = a0 & ~15u; tb < a1; tb += (uint32_t)kWChunks * 16u) {
-                const uint32_t n = w_tile_ranks(wf, tb, a0, a1, lane);
-                if (work && n) w_tile_calls(P, wf, flex, s_lut, jb, n, carry_cnt, ml_base, lane);
-                carry_cnt += n;
-                __syncwarp();
-            }
-            err = w_err(wf);
+            for (uint32_t tb = a0 & ~15u; tb < a1; tb += (uint32_t)kWChunks * 16u)
+                carry_cnt += w_fused_tile(P, R, T, s_lut, jb, tb, carry_cnt, ml_base, lane);
+            err = w_err(R);
             if (err) break;
+            if (lane == 0) { bd->n_calls = carry_cnt; bd->last1 = S.carry_sum; bd->ml_base = ml_base; }
+            __syncwarp();
             if (need_bm) {
-                w_implicit_block(P, wf, flex, s_lut, jb, carry_cnt, ml_base, lane);
-                err = w_err(wf);
+                w_fused_implicit(P, R, s_lut, jb, lane);
+                err = w_err(R);
                 if (err) break;
             }
             if (carry_cnt > 0) ml_base += carry_cnt * bd->K;                    // src/mod.c:1200
