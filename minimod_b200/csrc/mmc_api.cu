@@ -77,6 +77,8 @@ struct mmc_ctx {
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
     int flat_path = 1;                         // the flat kernel chain first (mmc_decode_flat.cuh)
+    uint32_t flat_sub = 16384;                 // reads per sub-batch of the chain (0: whole batch)
+    uint32_t flat_stage_calls = 960, flat_stage_index = 1536;   // shared-memory staging words per warp
     int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
     int w_minb = 3;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
     uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
@@ -255,7 +257,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
         max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
         const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
-        pool_need += 164 + 2ull * nc + 2 * (n_u4 + 2 + (L >> 6) + 2) + 2 * (n_u4 + 1) + 8;
+        pool_need += 164 + 2ull * nc + 2 * (n_u4 + 2 + (L >> 5) + 2) + 2 * (n_u4 + 1) + 24;
     }
     unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     if (grid == 0) grid = 1;
@@ -328,16 +330,27 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
 
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
     if (ctx->flat_path) {
-        const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
-        const unsigned sgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads - 1) / kFThreads, (uint64_t)ctx->sm_count * 8);
-        MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
-        MMC_LAUNCH(k_flat_index, rgrid, (unsigned)kFThreads, s.stream, P, F);
-        MMC_LAUNCH(k_flat_tile_sums, tgrid, (unsigned)kFThreads, s.stream, P, F);
-        MMC_LAUNCH(k_flat_scan, sgrid, (unsigned)kFThreads, s.stream, P, F);
-        MMC_LAUNCH(k_flat_tile_calls, tgrid, (unsigned)kFThreads, s.stream, P, F);
-        MMC_LAUNCH(k_flat_finish, rgrid, (unsigned)kFThreads, s.stream, P, F);
-        CU(ctx, cudaGetLastError());
-        ctx->tm.kernel_launches += 6;
+        // sub-batches keep the per-read scratch of one pass L2-resident between the kernels of the chain
+        const uint32_t sub = ctx->flat_sub ? ctx->flat_sub : n;
+        const size_t smem_calls = (size_t)kWLutSlots * 256 + (size_t)(kFThreads / 32) * (kWTileBytes + kWRead1Bytes + (size_t)ctx->flat_stage_calls * 4);
+        const size_t smem_index = (size_t)(kFThreads / 32) * (kWRead1Bytes + (size_t)ctx->flat_stage_index * 4);
+        for (uint32_t first = 0; first < n; first += sub) {
+            const uint32_t cnt = std::min<uint32_t>(sub, n - first);
+            F.read_first = first; F.read_count = cnt;
+            if (first) CU(ctx, cudaMemsetAsync(s.d_state + 4, 0, 16, s.stream));    // pool cursor, tile / dot counters
+            const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)cnt + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
+            const unsigned sgrid = (unsigned)std::min<uint64_t>(((uint64_t)cnt + kFThreads - 1) / kFThreads, (uint64_t)ctx->sm_count * 8);
+            MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
+            F.stage_words = ctx->flat_stage_index;
+            MMC_LAUNCH_SMEM(k_flat_index, rgrid, (unsigned)kFThreads, smem_index, s.stream, P, F);
+            MMC_LAUNCH(k_flat_tile_sums, tgrid, (unsigned)kFThreads, s.stream, P, F);
+            MMC_LAUNCH(k_flat_scan, sgrid, (unsigned)kFThreads, s.stream, P, F);
+            F.stage_words = ctx->flat_stage_calls;
+            MMC_LAUNCH_SMEM(k_flat_tile_calls, tgrid, (unsigned)kFThreads, smem_calls, s.stream, P, F);
+            MMC_LAUNCH(k_flat_finish, rgrid, (unsigned)kFThreads, s.stream, P, F);
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 6;
+        }
         P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7;          // what is left goes through k_decode_warp
     }
     if (ctx->warp_path) {
@@ -434,6 +447,8 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->flat_path = 0; }
         else if (!strcmp(e, "warp")) ctx->flat_path = 0;
     }
+    if (const char *e = getenv("MMC_FLAT_SUB")) { long v = atol(e); if (v >= 0) ctx->flat_sub = (uint32_t)v; }
+    if (const char *e = getenv("MMC_FLAT_STAGE")) { long v = atol(e); if (v >= 0 && v <= 6000) ctx->flat_stage_calls = (uint32_t)(v & ~3l); }
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->w_minb = v; }   // tuning
     ctx->w_arena_bytes = ctx->w_minb == 2 ? 14208u : ctx->w_minb == 3 ? 9344u : 6912u;   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
@@ -458,6 +473,12 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     int occ = 1;
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, ctx->threads, 0));
     ctx->ctas_per_sm = occ < 1 ? 1 : occ;
+    {
+        const size_t smem_calls = (size_t)kWLutSlots * 256 + (size_t)(kFThreads / 32) * (kWTileBytes + kWRead1Bytes + (size_t)ctx->flat_stage_calls * 4);
+        const size_t smem_index = (size_t)(kFThreads / 32) * (kWRead1Bytes + (size_t)ctx->flat_stage_index * 4);
+        CUC(cudaFuncSetAttribute(k_flat_tile_calls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_calls));
+        CUC(cudaFuncSetAttribute(k_flat_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_index));
+    }
     {
         const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
         int wocc = 1;

@@ -44,14 +44,36 @@ struct FlatParams {
     uint32_t *n_tiles;
     uint32_t *n_dot;                         // reads with '.' blocks to process (implicit calls)
     uint32_t *defer_list, *defer_n;          // reads left to k_decode_warp
+    uint32_t read_first, read_count;         // the sub-batch [read_first, read_first + read_count) these launches work on
+    uint32_t stage_words;                    // shared-memory words per warp for staging a read's scratch (tile_calls / index)
 };
+
+struct WRead1 {                              // WRead with room for one block: the shared-memory copy a tile works on
+    WState   st;
+    uint32_t semi[kWBlocks + 4];
+    WBlock   blk[1];
+};
+constexpr uint32_t kWRead1Bytes = (uint32_t)((sizeof(WRead1) + 15) / 16 * 16);
+constexpr uint32_t kWTileBytes = (uint32_t)((sizeof(WTile) + 15) / 16 * 16);
+
+// lane-parallel word copy (n words; both pointers 4-byte aligned)
+__device__ __forceinline__ void f_copy_words(uint32_t *dst, const uint32_t *src, uint32_t n, uint32_t lane) {
+    for (uint32_t i = lane; i < n; i += 32u) dst[i] = src[i];
+}
+// lane-parallel 16-byte copy (n words rounded up to 4; both pointers 16-byte aligned)
+__device__ __forceinline__ void f_copy_vec(uint32_t *dst, const uint32_t *src, uint32_t n, uint32_t lane) {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (uint32_t i = lane; i < ((n + 3u) >> 2); i += 32u) d4[i] = s4[i];
+}
 
 __device__ __forceinline__ uint32_t f_warp_id() { return (blockIdx.x * blockDim.x + threadIdx.x) >> 5; }
 __device__ __forceinline__ uint32_t f_n_warps() { return (gridDim.x * blockDim.x) >> 5; }
 
 __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t r = f_warp_id(); r < P.n_reads; r += f_n_warps()) {
+    for (uint32_t i = f_warp_id(); i < F.read_count; i += f_n_warps()) {
+        const uint32_t r = F.read_first + i;
         WRead *R = &F.reads[r];
         __syncwarp();
         const bool ok = w_setup_read(P, R, nullptr, 0u, &F.fa, F.defer_list, F.defer_n, r, lane);
@@ -84,9 +106,13 @@ __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant_
 }
 
 __global__ void __launch_bounds__(kFThreads) k_flat_index(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
+    MMC_DYN_SMEM(uint4, f_dyn_index);
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t r = f_warp_id(); r < P.n_reads; r += f_n_warps()) {
-        WRead *R = &F.reads[r];
+    uint8_t *mine = reinterpret_cast<uint8_t *>(f_dyn_index) + (size_t)(threadIdx.x >> 5) * (kWRead1Bytes + F.stage_words * 4u);
+    WRead1 *Rs = reinterpret_cast<WRead1 *>(mine);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(mine + kWRead1Bytes);
+    for (uint32_t i = f_warp_id(); i < F.read_count; i += f_n_warps()) {
+        WRead *R = &F.reads[F.read_first + i];
         const uint32_t n_blocks = R->st.n_blocks;
         for (uint32_t b = 0; b < n_blocks; ++b) {
             WBlock *bd = &R->blk[b];
@@ -94,8 +120,24 @@ __global__ void __launch_bounds__(kFThreads) k_flat_index(const __grid_constant_
             uint32_t from = b;                                              // an earlier block of the same class has it already
             for (uint32_t e = 0; e < b; ++e)
                 if (w_needs_index(&R->blk[e]) && R->blk[e].cls == bd->cls) { from = e; break; }
-            if (from == b) w_build_index(R, b, lane);
-            else if (lane == 0) { bd->cnt_cls = R->blk[from].cnt_cls; bd->rshift = R->blk[from].rshift; }
+            if (from != b) {
+                if (lane == 0) { bd->cnt_cls = R->blk[from].cnt_cls; bd->rshift = R->blk[from].rshift; }
+            } else {
+                const uint32_t words = R->st.n_ent + 2u + R->st.n_rd;
+                if (words <= F.stage_words) {                               // build in shared memory, store coalesced
+                    __syncwarp();
+                    f_copy_words(reinterpret_cast<uint32_t *>(&Rs->st), reinterpret_cast<const uint32_t *>(&R->st), sizeof(WState) / 4, lane);
+                    f_copy_words(reinterpret_cast<uint32_t *>(&Rs->blk[0]), reinterpret_cast<const uint32_t *>(bd), sizeof(WBlock) / 4, lane);
+                    __syncwarp();
+                    if (lane == 0) Rs->st.flex = stage - Rs->blk[0].o_idx;  // so that flex + o_idx is the staging area
+                    __syncwarp();
+                    w_build_index(reinterpret_cast<WRead *>(Rs), 0u, lane);
+                    f_copy_vec(R->st.flex_home + bd->o_idx, stage, words, lane);
+                    if (lane == 0) { bd->cnt_cls = Rs->blk[0].cnt_cls; bd->rshift = Rs->blk[0].rshift; }
+                } else {
+                    w_build_index(R, b, lane);
+                }
+            }
             __syncwarp();
         }
     }
@@ -118,8 +160,8 @@ __global__ void __launch_bounds__(kFThreads) k_flat_tile_sums(const __grid_const
 }
 
 __global__ void __launch_bounds__(kFThreads) k_flat_scan(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < P.n_reads; r += gridDim.x * blockDim.x) {
-        WRead *R = &F.reads[r];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.read_count; i += gridDim.x * blockDim.x) {
+        WRead *R = &F.reads[F.read_first + i];
         const uint32_t n_blocks = R->st.n_blocks;
         uint32_t ml_base = 0;
         for (uint32_t b = 0; b < n_blocks; ++b) {
@@ -137,21 +179,38 @@ __global__ void __launch_bounds__(kFThreads) k_flat_scan(const __grid_constant__
 }
 
 __global__ void __launch_bounds__(kFThreads) k_flat_tile_calls(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
-    __shared__ WTile s_tile[kFThreads / 32];
-    __shared__ uint8_t s_lut[kWLutSlots * 256];
+    MMC_DYN_SMEM(uint4, f_dyn_calls);
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(f_dyn_calls);
     w_stage_luts(P, s_lut);
     const uint32_t lane = threadIdx.x & 31u;
-    WTile *T = &s_tile[threadIdx.x >> 5];
+    uint8_t *mine = s_lut + kWLutSlots * 256 + (size_t)(threadIdx.x >> 5) * (kWTileBytes + kWRead1Bytes + F.stage_words * 4u);
+    WTile *T = reinterpret_cast<WTile *>(mine);
+    WRead1 *Rs = reinterpret_cast<WRead1 *>(mine + kWTileBytes);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(mine + kWTileBytes + kWRead1Bytes);
     const uint32_t n_tiles = *F.n_tiles < F.tile_cap ? *F.n_tiles : F.tile_cap;
     for (uint32_t t = f_warp_id(); t < n_tiles; t += f_n_warps()) {
         const FlatTile ft = F.tiles[t];
-        WRead *R = &F.reads[ft.read];
-        const WBlock *bd = &R->blk[ft.blk];
+        if (ft.cnt == 0u) continue;
+        WRead *Rg = &F.reads[ft.read];
+        // the read's state, this tile's block and (if it fits) the read's lookup arrays -> shared memory
         __syncwarp();
-        if (ft.cnt == 0u || !bd->any_req || R->st.err != 0u) continue;      // nothing to do / read already fatal
+        f_copy_words(reinterpret_cast<uint32_t *>(&Rs->st), reinterpret_cast<const uint32_t *>(&Rg->st), sizeof(WState) / 4, lane);
+        f_copy_words(reinterpret_cast<uint32_t *>(&Rs->blk[0]), reinterpret_cast<const uint32_t *>(&Rg->blk[ft.blk]), sizeof(WBlock) / 4, lane);
+        __syncwarp();
+        if (!Rs->blk[0].any_req || Rs->st.err != 0u) continue;              // nothing to do / read already fatal
+        const uint32_t n_stage = Rs->st.n_stage;
+        if (n_stage <= F.stage_words) {
+            f_copy_vec(stage, Rs->st.flex_home, n_stage, lane);
+            __syncwarp();
+            if (lane == 0) Rs->st.flex = stage;
+        }
+        __syncwarp();
+        WRead *R = reinterpret_cast<WRead *>(Rs);
         uint32_t sum = 0;
-        const uint32_t n = w_tile_ranks(R, T, ft.tb, bd->hdr_end, bd->end, ft.carry_sum, &sum, lane);
-        w_tile_calls(P, R, T, s_lut, ft.blk, n, ft.carry_cnt, bd->ml_base, lane);
+        const uint32_t n = w_tile_ranks(R, T, ft.tb, Rs->blk[0].hdr_end, Rs->blk[0].end, ft.carry_sum, &sum, lane);
+        w_tile_calls(P, R, T, s_lut, 0u, ft.blk, n, ft.carry_cnt, Rs->blk[0].ml_base, lane);
+        __syncwarp();
+        if (lane == 0 && Rs->st.err != 0u) atomicCAS(&Rg->st.err, 0u, Rs->st.err);
     }
 }
 
@@ -160,7 +219,8 @@ __global__ void __launch_bounds__(kFThreads) k_flat_finish(const __grid_constant
     w_stage_luts(P, s_lut);
     const uint32_t lane = threadIdx.x & 31u;
     const bool dots = *F.n_dot != 0u;
-    for (uint32_t r = f_warp_id(); r < P.n_reads; r += f_n_warps()) {
+    for (uint32_t i = f_warp_id(); i < F.read_count; i += f_n_warps()) {
+        const uint32_t r = F.read_first + i;
         WRead *R = &F.reads[r];
         const uint32_t n_blocks = R->st.n_blocks;
         if (n_blocks == 0u) continue;

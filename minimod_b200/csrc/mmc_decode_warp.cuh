@@ -69,7 +69,9 @@ struct WState {                              // warp-uniform state of the read b
     const uint8_t  *seq, *mm, *ml;
     const uint32_t *ref2, *excm;
     unsigned long long *cells;
-    uint32_t *flex;                          // cq | cr | dir | idx | rd | bitmap words of this read
+    uint32_t *flex;                          // dir | cq | cr | idx+rd per class | bitmaps of this read (may be a staged copy)
+    uint32_t *flex_home;                     // where those words really live: the bitmaps are always updated there
+    uint32_t n_stage;                        // words before the bitmaps
     uint32_t r, L, n_cig, mm_len, ml_len, rev, hp, ref_len;
     int32_t  tid, pos;
     uint32_t o_cq, o_cr, o_dir;              // word offsets into flex
@@ -569,17 +571,18 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
     uint32_t gshift = 8;
     while (((L >> gshift) + 2u) > 160u) ++gshift;
     const uint32_t n_dir = (L >> gshift) + 2u;
-    const uint32_t n_rd = (L >> 6) + 2u;
+    const uint32_t n_rd = (L >> 5) + 2u;
     const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
     const uint32_t n_idx = fa ? (uint32_t)__popc(cls_set) : (idx_mask ? 1u : 0u);
     const uint32_t n_bm = fa ? (uint32_t)__popc(bm_mask) : (bm_mask ? 1u : 0u);
     const uint32_t cap = fa ? (1u << 20) : flex_words;                               // flat: sample only absurdly large reads
     uint32_t cshift = 0, ishift = 0, n_samp, n_ent, need;
+    auto a4 = [](uint32_t x) { return (x + 3u) & ~3u; };
     for (;;) {
         n_samp = (n_cig + (1u << cshift) - 1u) >> cshift;
         if (n_samp == 0u) n_samp = 1u;
         n_ent = (n_u4 + (1u << ishift) - 1u) >> ishift;
-        need = n_dir + 2u * n_samp + n_idx * (n_ent + 2u + n_rd) + n_bm * bm_words;
+        need = a4(n_dir + 2u * n_samp) + n_idx * a4(n_ent + 2u + n_rd) + n_bm * a4(bm_words);   // 16-byte aligned pieces
         if (need <= cap) break;
         if (cshift >= (uint32_t)kWMaxCShift && ishift >= (uint32_t)kWMaxIShift) { w_defer(defer_list, defer_n, r, lane); return false; }
         if ((2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
@@ -592,9 +595,9 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
         if (base + need > fa->cap) { w_defer(defer_list, defer_n, r, lane); return false; }
         flex = fa->pool + base;
     }
-    const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = o_cr + n_samp;
+    const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = a4(o_cr + n_samp);
     if (lane == 0) {
-        S.flex = flex;
+        S.flex = flex; S.flex_home = flex;
         S.o_dir = o_dir; S.o_cq = o_cq; S.o_cr = o_cr;
         S.cshift = cshift; S.gshift = gshift; S.ishift = ishift; S.n_samp = n_samp; S.n_ent = n_ent; S.n_u4 = n_u4; S.n_rd = n_rd;
         // per block: where its class index / bitmap live
@@ -605,15 +608,16 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
                 const uint32_t c = bd.cls;
                 if (!fa) { bd.o_idx = o_var; bd.o_rd = o_var + n_ent + 2u; }
                 else {
-                    if (!((seen >> c) & 1u)) { cls_off[c] = next; next += n_ent + 2u + n_rd; seen |= 1u << c; }
+                    if (!((seen >> c) & 1u)) { cls_off[c] = next; next += a4(n_ent + 2u + n_rd); seen |= 1u << c; }
                     bd.o_idx = cls_off[c]; bd.o_rd = cls_off[c] + n_ent + 2u;
                 }
             }
         }
-        if (!fa) next = o_var + n_idx * (n_ent + 2u + n_rd);
+        if (!fa) next = o_var + n_idx * a4(n_ent + 2u + n_rd);
+        S.n_stage = next;
         for (uint32_t b = 0; b < n_blocks; ++b) {
             WBlock &bd = R->blk[b];
-            if ((bm_mask >> b) & 1u) { bd.o_bm = next; if (fa) next += bm_words; }
+            if ((bm_mask >> b) & 1u) { bd.o_bm = next; if (fa) next += a4(bm_words); }
         }
     }
 
@@ -829,7 +833,7 @@ template <bool C0>
 __device__ __forceinline__ void w_pass_select(WRead *R, WTile *T, const WBlock *bd, uint32_t pat, uint32_t n, uint32_t need_bm, uint32_t lane) {
     const WState &S = R->st;
     const uint32_t rev = S.rev, cnt_cls = bd->cnt_cls;
-    uint32_t *bm = S.flex + bd->o_bm;
+    uint32_t *bm = S.flex_home + bd->o_bm;
     for (uint32_t c = lane; c < n; c += 32u) {
         const uint32_t r0 = T->rank[c];
         if (r0 >= cnt_cls) { w_raise(R, kErrMMRank); T->rank[c] = kNoCall; continue; }     // src/mod.c:1116
@@ -839,16 +843,16 @@ __device__ __forceinline__ void w_pass_select(WRead *R, WTile *T, const WBlock *
     }
 }
 
-__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, uint32_t jb,
+__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, uint32_t slot, uint32_t jb,
                                              uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
-    const WBlock *bd = &R->blk[jb];
+    const WBlock *bd = &R->blk[slot];                              // jb: the block's ordinal in the read (view row order)
     const uint32_t cls = bd->cls, need_bm = bd->dot;
     const uint32_t pat = class_pat(cls), rd_code = cls >= 1u && cls <= 3u ? cls : 4u;
     // ---- select
     if (bd->is_n) {                                               // src/mod.c:1102-1107
         const uint32_t L = S.L, rev = S.rev;
-        uint32_t *bm = S.flex + bd->o_bm;
+        uint32_t *bm = S.flex_home + bd->o_bm;
         for (uint32_t c = lane; c < n; c += 32u) {
             const uint32_t rank = T->rank[c];
             if (rank >= L) { w_raise(R, kErrMMRank); T->rank[c] = kNoCall; continue; }
@@ -882,7 +886,7 @@ __device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WT
 __device__ __forceinline__ void w_implicit_block(const DecodeParams &P, WRead *R, const uint8_t *s_lut, uint32_t jb, uint32_t lane) {
     const WState &S = R->st;
     const WBlock *bd = &R->blk[jb];
-    const uint32_t *bm = S.flex + bd->o_bm, *idx = S.flex + bd->o_idx;
+    const uint32_t *bm = S.flex_home + bd->o_bm, *idx = S.flex + bd->o_idx;
     const uint32_t cnt_cls = bd->cnt_cls, ml_base = bd->ml_base;
     if (bd->is_n) {
         const uint32_t last1 = bd->n_calls > 0 ? bd->last1 : 0u;                    // last + 1
@@ -930,7 +934,7 @@ __device__ __noinline__ uint32_t w_fused_tile(const DecodeParams &P, WRead *R, W
     const WBlock *bd = &R->blk[jb];
     uint32_t sum = 0;
     const uint32_t n = w_tile_ranks(R, T, tb, bd->hdr_end, bd->end, S.carry_sum, &sum, lane);
-    if (bd->any_req && n) w_tile_calls(P, R, T, s_lut, jb, n, carry_cnt, ml_base, lane);
+    if (bd->any_req && n) w_tile_calls(P, R, T, s_lut, jb, jb, n, carry_cnt, ml_base, lane);
     __syncwarp();
     if (lane == 0) S.carry_sum = sat_add(S.carry_sum, sum);
     __syncwarp();
@@ -981,7 +985,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
             }
             if (need_bm) {
                 const uint32_t words = ((S.L + 31u) >> 5) + 1u;
-                for (uint32_t w = lane; w < words; w += 32u) flex[bd->o_bm + w] = 0;
+                for (uint32_t w = lane; w < words; w += 32u) S.flex_home[bd->o_bm + w] = 0;
             }
             if (lane == 0) S.carry_sum = 0;
             __syncwarp();
