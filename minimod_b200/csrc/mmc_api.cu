@@ -76,7 +76,8 @@ struct mmc_ctx {
     std::vector<Slot> slots;
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
-    int flat_path = 1;                         // the flat kernel chain first (mmc_decode_flat.cuh)
+    int flat_path = 0;                         // the flat kernel chain first (mmc_decode_flat.cuh)
+    int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     uint32_t flat_sub = 16384;                 // reads per sub-batch of the chain (0: whole batch)
     uint32_t flat_stage_calls = 960, flat_stage_index = 1536;   // shared-memory staging words per warp
     int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
@@ -188,7 +189,7 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaMalloc((void **)&s.d_state, 128));
     CU(ctx, cudaMallocHost((void **)&s.h_state, 128));
     CU(ctx, cudaMalloc((void **)&s.d_defer_flat, sizeof(uint32_t) * std::max<size_t>(1, R)));
-    if (ctx->flat_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
+    if (ctx->flat_path || ctx->split_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
     CU(ctx, cudaMalloc((void **)&s.d_defer, sizeof(uint32_t) * std::max<size_t>(1, R)));
     if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
     mmc_batch_t &b = s.pub;
@@ -304,7 +305,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     FlatParams F;
     memset(&F, 0, sizeof(F));
     unsigned tgrid = 1;
-    if (ctx->flat_path) {
+    if (ctx->flat_path || ctx->split_path) {
         const size_t tile_need = (size_t)(b.mm_used / (kWChunks * 16)) + 2 * (size_t)kWBlocks * n + 64;
         if (pool_need > s.pool_words || tile_need > s.tile_cap) {
             CU(ctx, cudaStreamSynchronize(s.stream));
@@ -361,9 +362,28 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         unsigned wgrid = (unsigned)std::min<uint64_t>((warps + kWThreads / 32 - 1) / (kWThreads / 32), (uint64_t)ctx->sm_count * ctx->w_ctas_per_sm);
         if (wgrid == 0) wgrid = 1;
         const size_t wsmem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
-        if (ctx->w_minb == 2) MMC_LAUNCH_SMEM(k_decode_warp<2>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
-        else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM(k_decode_warp<3>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
-        else MMC_LAUNCH_SMEM(k_decode_warp<4>, wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W);
+        PreParams Q; Q.reads = nullptr; Q.n = 0;
+        if (ctx->split_path) {
+            // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
+            F.fa.arena_words = (ctx->w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
+            F.read_first = 0; F.read_count = n;
+            const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
+            MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 1;
+            Q.reads = s.d_reads; Q.n = n;
+            if (ctx->w_minb == 2) MMC_LAUNCH_SMEM((k_decode_warp<2, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+            else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM((k_decode_warp<3, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+            else MMC_LAUNCH_SMEM((k_decode_warp<4, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 1;
+            // reads k_flat_setup could not prepare go through the self-contained kernel below
+            P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7; P.work_counter = st32 + 12;
+            Q.reads = nullptr; Q.n = 0;
+        }
+        if (ctx->w_minb == 2) MMC_LAUNCH_SMEM((k_decode_warp<2, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+        else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM((k_decode_warp<3, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+        else MMC_LAUNCH_SMEM((k_decode_warp<4, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
         CU(ctx, cudaGetLastError());
         ctx->tm.kernel_launches += 1;
         P.read_list = s.d_defer; P.read_list_n = st32 + 5; P.work_counter = st32 + 6;
@@ -444,8 +464,10 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
     }
     if (const char *e = getenv("MMC_DECODE_PATH")) {         // "general": CTA-per-read kernel only (test hook / A-B timing)
-        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->flat_path = 0; }
-        else if (!strcmp(e, "warp")) ctx->flat_path = 0;
+        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->flat_path = 0; ctx->split_path = 0; }
+        else if (!strcmp(e, "warp")) { ctx->flat_path = 0; ctx->split_path = 0; }
+        else if (!strcmp(e, "flat")) { ctx->flat_path = 1; ctx->split_path = 0; }
+        else if (!strcmp(e, "split")) { ctx->flat_path = 0; ctx->split_path = 1; }
     }
     if (const char *e = getenv("MMC_FLAT_SUB")) { long v = atol(e); if (v >= 0) ctx->flat_sub = (uint32_t)v; }
     if (const char *e = getenv("MMC_FLAT_STAGE")) { long v = atol(e); if (v >= 0 && v <= 6000) ctx->flat_stage_calls = (uint32_t)(v & ~3l); }
@@ -482,16 +504,14 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     {
         const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
         int wocc = 1;
-        if (ctx->w_minb == 2) {
-            CUC(cudaFuncSetAttribute(k_decode_warp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, k_decode_warp<2>, kWThreads, smem));
-        } else if (ctx->w_minb == 3) {
-            CUC(cudaFuncSetAttribute(k_decode_warp<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, k_decode_warp<3>, kWThreads, smem));
-        } else {
-            CUC(cudaFuncSetAttribute(k_decode_warp<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, k_decode_warp<4>, kWThreads, smem));
-        }
+#define MMC_WARP_ATTR(MB)                                                                                                        \
+        do {                                                                                                                     \
+            CUC(cudaFuncSetAttribute((k_decode_warp<MB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+            CUC(cudaFuncSetAttribute((k_decode_warp<MB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, (k_decode_warp<MB, true>), kWThreads, smem));               \
+        } while (0)
+        if (ctx->w_minb == 2) MMC_WARP_ATTR(2); else if (ctx->w_minb == 3) MMC_WARP_ATTR(3); else MMC_WARP_ATTR(4);
+#undef MMC_WARP_ATTR
         ctx->w_ctas_per_sm = wocc < 1 ? 1 : wocc;
     }
 

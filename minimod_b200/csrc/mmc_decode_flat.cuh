@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant_
         const bool ok = w_setup_read(P, R, nullptr, 0u, &F.fa, F.defer_list, F.defer_n, r, lane);
         __syncwarp();
         if (!ok) { if (lane == 0) R->st.n_blocks = 0; continue; }           // not ours (or fatal): later kernels skip it
+        if (F.fa.arena_words != 0u) continue;                               // split mode: k_decode_warp<PRE> takes it from here
         const uint32_t n_blocks = R->st.n_blocks, bm_words = ((R->st.L + 31u) >> 5) + 1u;
         uint32_t any_dot = 0;
         for (uint32_t b = 0; b < n_blocks; ++b) {

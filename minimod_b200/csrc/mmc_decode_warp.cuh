@@ -110,6 +110,8 @@ struct FlatAlloc {                           // flat path: bump allocator over a
     uint32_t *pool;
     unsigned long long *cursor;
     unsigned long long cap;
+    uint32_t arena_words;                    // != 0: "split" mode -- only dir|cq|cr go to the pool, the index and the
+                                             // bitmap are laid out for a shared-memory arena of that many words
 };
 
 // ---------------------------------------------------------------------------------------
@@ -573,9 +575,10 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
     const uint32_t n_dir = (L >> gshift) + 2u;
     const uint32_t n_rd = (L >> 5) + 2u;
     const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
-    const uint32_t n_idx = fa ? (uint32_t)__popc(cls_set) : (idx_mask ? 1u : 0u);
-    const uint32_t n_bm = fa ? (uint32_t)__popc(bm_mask) : (bm_mask ? 1u : 0u);
-    const uint32_t cap = fa ? (1u << 20) : flex_words;                               // flat: sample only absurdly large reads
+    const bool per_block = fa && fa->arena_words == 0u;                              // flat: one index per class, one bitmap per block
+    const uint32_t n_idx = per_block ? (uint32_t)__popc(cls_set) : (idx_mask ? 1u : 0u);
+    const uint32_t n_bm = per_block ? (uint32_t)__popc(bm_mask) : (bm_mask ? 1u : 0u);
+    const uint32_t cap = per_block ? (1u << 20) : fa ? fa->arena_words : flex_words; // flat: sample only absurdly large reads
     uint32_t cshift = 0, ishift = 0, n_samp, n_ent, need;
     auto a4 = [](uint32_t x) { return (x + 3u) & ~3u; };
     for (;;) {
@@ -589,10 +592,11 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
         else ++ishift;
     }
     if (fa) {                                                                        // bump-allocate from the global pool
+        const uint32_t take = per_block ? need : a4(n_dir + 2u * n_samp);
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(fa->cursor, (unsigned long long)((need + 3u) & ~3u));
+        if (lane == 0) base = atomicAdd(fa->cursor, (unsigned long long)take);
         base = ((unsigned long long)__shfl_sync(kFull, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)base, 0);
-        if (base + need > fa->cap) { w_defer(defer_list, defer_n, r, lane); return false; }
+        if (base + take > fa->cap) { w_defer(defer_list, defer_n, r, lane); return false; }
         flex = fa->pool + base;
     }
     const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = a4(o_cr + n_samp);
@@ -606,18 +610,18 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
             WBlock &bd = R->blk[b];
             if ((idx_mask >> b) & 1u) {
                 const uint32_t c = bd.cls;
-                if (!fa) { bd.o_idx = o_var; bd.o_rd = o_var + n_ent + 2u; }
+                if (!per_block) { bd.o_idx = o_var; bd.o_rd = o_var + n_ent + 2u; }
                 else {
                     if (!((seen >> c) & 1u)) { cls_off[c] = next; next += a4(n_ent + 2u + n_rd); seen |= 1u << c; }
                     bd.o_idx = cls_off[c]; bd.o_rd = cls_off[c] + n_ent + 2u;
                 }
             }
         }
-        if (!fa) next = o_var + n_idx * a4(n_ent + 2u + n_rd);
-        S.n_stage = next;
+        if (!per_block) next = o_var + n_idx * a4(n_ent + 2u + n_rd);
+        S.n_stage = per_block ? next : o_var;
         for (uint32_t b = 0; b < n_blocks; ++b) {
             WBlock &bd = R->blk[b];
-            if ((bm_mask >> b) & 1u) { bd.o_bm = next; if (fa) next += a4(bm_words); }
+            if ((bm_mask >> b) & 1u) { bd.o_bm = next; if (per_block) next += a4(bm_words); }
         }
     }
 
@@ -946,8 +950,14 @@ __device__ __noinline__ void w_fused_implicit(const DecodeParams &P, WRead *R, c
 
 // MINB = resident CTAs per SM the register allocation is bounded for (2: 128 regs, 3: 80, 4: 64);
 // the host picks one (and the matching arena size) per context.
-template <int MINB>
-__global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_constant__ DecodeParams P, const __grid_constant__ WarpParams W) {
+// PRE  = the reads were prepared by k_flat_setup in "split" mode (mmc_decode_flat.cuh): this kernel then
+//        only copies WRead + dir|cq|cr into its arena instead of running w_setup_read, which keeps the
+//        header parser and the CIGAR scan out of its instruction footprint.
+struct PreParams { const WRead *reads; uint32_t n; };
+
+template <int MINB, bool PRE>
+__global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_constant__ DecodeParams P, const __grid_constant__ WarpParams W,
+                                                                 const __grid_constant__ PreParams Q) {
     MMC_DYN_SMEM(uint4, w_dyn);
     uint8_t *s_lut = reinterpret_cast<uint8_t *>(w_dyn);
     w_stage_luts(P, s_lut);
@@ -963,12 +973,30 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
         uint32_t r = 0;
         if (lane == 0) {
             r = atomicAdd(P.work_counter, 1u);
-            if (P.read_list) r = r < *P.read_list_n ? P.read_list[r] : 0xffffffffu;     // reads deferred by the flat path
+            if (!PRE && P.read_list) r = r < *P.read_list_n ? P.read_list[r] : 0xffffffffu;   // reads deferred by an earlier kernel
         }
         r = __shfl_sync(kFull, r, 0);
-        if (r >= P.n_reads) break;
         __syncwarp();
-        if (!w_setup_read(P, R, flex, flex_words, nullptr, W.defer_list, W.defer_n, r, lane)) continue;
+        if (PRE) {
+            if (r >= Q.n) break;
+            const WRead *G = &Q.reads[r];
+            const uint32_t nb = G->st.n_blocks;
+            if (nb == 0u) continue;                               // deferred or fatal in k_flat_setup
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(G);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(R);
+            const uint32_t words = (uint32_t)((sizeof(WState) + sizeof(uint32_t) * (kWBlocks + 4) + sizeof(WBlock) * nb) / 4);
+            for (uint32_t i = lane; i < words; i += 32u) dst[i] = src[i];
+            __syncwarp();
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(S.flex_home);
+            uint4 *d4 = reinterpret_cast<uint4 *>(flex);
+            for (uint32_t i = lane; i < ((S.n_stage + 3u) >> 2); i += 32u) d4[i] = s4[i];
+            __syncwarp();
+            if (lane == 0) { S.flex = flex; S.flex_home = flex; S.cur_cls = 0xffu; S.cur_blk = 0; }
+            __syncwarp();
+        } else {
+            if (r >= P.n_reads) break;
+            if (!w_setup_read(P, R, flex, flex_words, nullptr, W.defer_list, W.defer_n, r, lane)) continue;
+        }
 
         // ---- blocks in order
         const uint32_t n_blocks = S.n_blocks;
@@ -1003,7 +1031,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
             }
             if (carry_cnt > 0) ml_base += carry_cnt * bd->K;                    // src/mod.c:1200
         }
-        if (err) w_report(P, r, err, lane);
+        if (err) w_report(P, S.r, err, lane);
     }
 }
 
