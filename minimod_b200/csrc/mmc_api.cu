@@ -48,7 +48,6 @@ struct Slot {
     uint32_t *d_defer_flat = nullptr;          // reads the flat kernels left to k_decode_warp
     WRead *d_reads = nullptr;                  // flat path: per-read state
     uint32_t *d_pool = nullptr; size_t pool_words = 0;      // flat path: scratch pool
-    FlatTile *d_tiles = nullptr; size_t tile_cap = 0;       // flat path: text tiles
     unsigned long long *h_state = nullptr;     // pinned mirror
     ViewDev *d_view = nullptr;
     uint32_t *d_scratch = nullptr;
@@ -76,10 +75,7 @@ struct mmc_ctx {
     std::vector<Slot> slots;
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
-    int flat_path = 0;                         // the flat kernel chain first (mmc_decode_flat.cuh)
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
-    uint32_t flat_sub = 16384;                 // reads per sub-batch of the chain (0: whole batch)
-    uint32_t flat_stage_calls = 960, flat_stage_index = 1536;   // shared-memory staging words per warp
     int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
     int w_minb = 3;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
     uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
@@ -189,7 +185,7 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaMalloc((void **)&s.d_state, 128));
     CU(ctx, cudaMallocHost((void **)&s.h_state, 128));
     CU(ctx, cudaMalloc((void **)&s.d_defer_flat, sizeof(uint32_t) * std::max<size_t>(1, R)));
-    if (ctx->flat_path || ctx->split_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
+    if (ctx->split_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
     CU(ctx, cudaMalloc((void **)&s.d_defer, sizeof(uint32_t) * std::max<size_t>(1, R)));
     if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
     mmc_batch_t &b = s.pub;
@@ -258,7 +254,8 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
         max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
         const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
-        pool_need += 164 + 2ull * nc + 2 * (n_u4 + 2 + (L >> 5) + 2) + 2 * (n_u4 + 1) + 24;
+        pool_need += 164 + 2ull * nc + 8;      // dir | cq | cr
+        (void)n_u4;
     }
     unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     if (grid == 0) grid = 1;
@@ -304,56 +301,20 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
 
     FlatParams F;
     memset(&F, 0, sizeof(F));
-    unsigned tgrid = 1;
-    if (ctx->flat_path || ctx->split_path) {
-        const size_t tile_need = (size_t)(b.mm_used / (kWChunks * 16)) + 2 * (size_t)kWBlocks * n + 64;
-        if (pool_need > s.pool_words || tile_need > s.tile_cap) {
+    if (ctx->split_path) {
+        if (pool_need > s.pool_words) {
             CU(ctx, cudaStreamSynchronize(s.stream));
-            if (pool_need > s.pool_words) {
-                if (s.d_pool) CU(ctx, cudaFree(s.d_pool));
-                s.d_pool = nullptr; s.pool_words = 0;
-                CU(ctx, cudaMalloc((void **)&s.d_pool, pool_need * 4));
-                s.pool_words = pool_need;
-            }
-            if (tile_need > s.tile_cap) {
-                if (s.d_tiles) CU(ctx, cudaFree(s.d_tiles));
-                s.d_tiles = nullptr; s.tile_cap = 0;
-                CU(ctx, cudaMalloc((void **)&s.d_tiles, tile_need * sizeof(FlatTile)));
-                s.tile_cap = tile_need;
-            }
+            if (s.d_pool) CU(ctx, cudaFree(s.d_pool));
+            s.d_pool = nullptr; s.pool_words = 0;
+            CU(ctx, cudaMalloc((void **)&s.d_pool, pool_need * 4));
+            s.pool_words = pool_need;
         }
         F.reads = s.d_reads;
         F.fa.pool = s.d_pool; F.fa.cursor = s.d_state + 4; F.fa.cap = s.pool_words;
-        F.tiles = s.d_tiles; F.tile_cap = (uint32_t)std::min<size_t>(s.tile_cap, 0xffffffffu); F.n_tiles = st32 + 10; F.n_dot = st32 + 11;
         F.defer_list = s.d_defer_flat; F.defer_n = st32 + 7;
-        tgrid = (unsigned)std::min<uint64_t>((tile_need + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 8);
     }
 
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
-    if (ctx->flat_path) {
-        // sub-batches keep the per-read scratch of one pass L2-resident between the kernels of the chain
-        const uint32_t sub = ctx->flat_sub ? ctx->flat_sub : n;
-        const size_t smem_calls = (size_t)kWLutSlots * 256 + (size_t)(kFThreads / 32) * (kWTileBytes + kWRead1Bytes + (size_t)ctx->flat_stage_calls * 4);
-        const size_t smem_index = (size_t)(kFThreads / 32) * (kWRead1Bytes + (size_t)ctx->flat_stage_index * 4);
-        for (uint32_t first = 0; first < n; first += sub) {
-            const uint32_t cnt = std::min<uint32_t>(sub, n - first);
-            F.read_first = first; F.read_count = cnt;
-            if (first) CU(ctx, cudaMemsetAsync(s.d_state + 4, 0, 16, s.stream));    // pool cursor, tile / dot counters
-            const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)cnt + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
-            const unsigned sgrid = (unsigned)std::min<uint64_t>(((uint64_t)cnt + kFThreads - 1) / kFThreads, (uint64_t)ctx->sm_count * 8);
-            MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
-            F.stage_words = ctx->flat_stage_index;
-            MMC_LAUNCH_SMEM(k_flat_index, rgrid, (unsigned)kFThreads, smem_index, s.stream, P, F);
-            MMC_LAUNCH(k_flat_tile_sums, tgrid, (unsigned)kFThreads, s.stream, P, F);
-            MMC_LAUNCH(k_flat_scan, sgrid, (unsigned)kFThreads, s.stream, P, F);
-            F.stage_words = ctx->flat_stage_calls;
-            MMC_LAUNCH_SMEM(k_flat_tile_calls, tgrid, (unsigned)kFThreads, smem_calls, s.stream, P, F);
-            MMC_LAUNCH(k_flat_finish, rgrid, (unsigned)kFThreads, s.stream, P, F);
-            CU(ctx, cudaGetLastError());
-            ctx->tm.kernel_launches += 6;
-        }
-        P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7;          // what is left goes through k_decode_warp
-    }
     if (ctx->warp_path) {
         // fast path: one warp per read; reads that do not fit a warp's shared-memory arena go to the list
         WarpParams W;
@@ -366,7 +327,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         if (ctx->split_path) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
             F.fa.arena_words = (ctx->w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
-            F.read_first = 0; F.read_count = n;
+            F.read_count = n;
             const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
             MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
             CU(ctx, cudaGetLastError());
@@ -411,7 +372,7 @@ int wait_slot(mmc_ctx *ctx, Slot &s) {
     if (s.timed) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) ctx->tm.decode_ms += ms;
-        ctx->tm.deferred_reads += ((const uint32_t *)s.h_state)[5] + (ctx->warp_path ? 0 : ((const uint32_t *)s.h_state)[7]);
+        ctx->tm.deferred_reads += ((const uint32_t *)s.h_state)[5];
         ctx->tm.flat_deferred_reads += ((const uint32_t *)s.h_state)[7];
         s.timed = false;
     }
@@ -464,13 +425,10 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
     }
     if (const char *e = getenv("MMC_DECODE_PATH")) {         // "general": CTA-per-read kernel only (test hook / A-B timing)
-        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->flat_path = 0; ctx->split_path = 0; }
-        else if (!strcmp(e, "warp")) { ctx->flat_path = 0; ctx->split_path = 0; }
-        else if (!strcmp(e, "flat")) { ctx->flat_path = 1; ctx->split_path = 0; }
-        else if (!strcmp(e, "split")) { ctx->flat_path = 0; ctx->split_path = 1; }
+        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->split_path = 0; }
+        else if (!strcmp(e, "warp")) ctx->split_path = 0;
+        else if (!strcmp(e, "split")) ctx->split_path = 1;
     }
-    if (const char *e = getenv("MMC_FLAT_SUB")) { long v = atol(e); if (v >= 0) ctx->flat_sub = (uint32_t)v; }
-    if (const char *e = getenv("MMC_FLAT_STAGE")) { long v = atol(e); if (v >= 0 && v <= 6000) ctx->flat_stage_calls = (uint32_t)(v & ~3l); }
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->w_minb = v; }   // tuning
     ctx->w_arena_bytes = ctx->w_minb == 2 ? 14208u : ctx->w_minb == 3 ? 9344u : 6912u;   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
@@ -495,12 +453,6 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     int occ = 1;
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, ctx->threads, 0));
     ctx->ctas_per_sm = occ < 1 ? 1 : occ;
-    {
-        const size_t smem_calls = (size_t)kWLutSlots * 256 + (size_t)(kFThreads / 32) * (kWTileBytes + kWRead1Bytes + (size_t)ctx->flat_stage_calls * 4);
-        const size_t smem_index = (size_t)(kFThreads / 32) * (kWRead1Bytes + (size_t)ctx->flat_stage_index * 4);
-        CUC(cudaFuncSetAttribute(k_flat_tile_calls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_calls));
-        CUC(cudaFuncSetAttribute(k_flat_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_index));
-    }
     {
         const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
         int wocc = 1;
@@ -609,7 +561,6 @@ void mmc_destroy(mmc_ctx *ctx) {
         if (s.d_defer_flat) cudaFree(s.d_defer_flat);
         if (s.d_reads) cudaFree(s.d_reads);
         if (s.d_pool) cudaFree(s.d_pool);
-        if (s.d_tiles) cudaFree(s.d_tiles);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.ev_h0) cudaEventDestroy(s.ev_h0);
         if (s.ev_h1) cudaEventDestroy(s.ev_h1);

@@ -100,6 +100,18 @@ struct WFixed {                              // fixed part of a warp's arena on 
     WTile tl;
 };
 
+struct WArena { uint8_t *s_lut; WRead *R; WTile *T; uint32_t *flex; };
+__device__ __forceinline__ WArena w_arena(uint32_t aoff) {
+    MMC_DYN_SMEM(uint4, w_dyn);
+    uint8_t *base = reinterpret_cast<uint8_t *>(w_dyn);
+    WArena A;
+    A.s_lut = base;
+    WFixed *wf = reinterpret_cast<WFixed *>(base + aoff);
+    A.R = &wf->rd; A.T = &wf->tl;
+    A.flex = reinterpret_cast<uint32_t *>(base + aoff + sizeof(WFixed));
+    return A;
+}
+
 struct WarpParams {
     uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(WFixed) + 256
     uint32_t *defer_list;                    // reads left to k_decode
@@ -176,7 +188,22 @@ __device__ __forceinline__ uint32_t count_u4_tail(uint4 v, uint32_t pat, uint32_
                       __popc(valid_flags(class_flags<C0>(v.z, pat), nv > 16u ? nv - 16u : 0u)) +
                       __popc(valid_flags(class_flags<C0>(v.w, pat), nv > 24u ? nv - 24u : 0u)));
 }
-__device__ __forceinline__ uint4 ld16(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+// global-memory accesses spelled out: the pointers come out of structs in shared memory, where the
+// compiler cannot see their address space and would emit generic LD / ATOM with run-time space checks
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t ldg8(const uint8_t *p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v) {
+#ifdef MMC_EMUL
+    *p += v;
+#else
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+
+// The fused kernels' dynamic shared memory: [call LUTs][arena of warp 0][arena of warp 1]...  Non-inlined
+// phase functions get a warp's arena as a byte OFFSET and rebuild their pointers from the array itself,
+// so that every access compiles to LDS/STS with an immediate offset.
 
 __device__ __forceinline__ void w_raise(WRead *R, uint32_t code) { atomicCAS(&R->st.err, 0u, code); }
 __device__ __forceinline__ uint32_t w_err(WRead *R) {
@@ -191,11 +218,10 @@ __device__ __forceinline__ uint32_t w_err(WRead *R) {
 // cq[s] = (read bases consumed before op s<<cshift) << 4 | that op's type; cr[s] = reference
 // bases consumed before it.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, uint32_t q) {
+__device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, const uint32_t *flex, uint32_t q) {
     AlnHit h; h.aln = -1; h.ins = -1; h.insoff = 0;
     const uint32_t total_q = S.total_q;
     if (q >= total_q) return h;
-    const uint32_t *flex = S.flex;
     const uint32_t *dir = flex + S.o_dir, *cq = flex + S.o_cq;
     const uint32_t g = S.gshift, b = q >> g;
     uint32_t lo = dir[b];
@@ -212,7 +238,7 @@ __device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, uint32_t q) {
         const uint32_t *cig = S.cig;
         const uint32_t n_cig = S.n_cig;
         for (uint32_t o = lo << cshift; o < n_cig; ++o) {
-            const uint32_t w = cig[o], len = w >> 4;
+            const uint32_t w = ldg32(cig + o), len = w >> 4;
             op = w & 15u;
             const bool aln = op == 0u || op == 7u || op == 8u;
             const uint32_t ql = (aln || op == 1u || op == 4u) ? len : 0u;
@@ -233,8 +259,7 @@ __device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, uint32_t q) {
 // ---------------------------------------------------------------------------------------
 struct SelProbe { uint32_t u, rem; uint4 v; };
 template <bool C0>
-__device__ __forceinline__ SelProbe w_select_probe(const WState &S, const WBlock *bd, uint32_t pat, uint32_t k) {
-    const uint32_t *flex = S.flex;
+__device__ __forceinline__ SelProbe w_select_probe(const WState &S, const uint32_t *flex, const WBlock *bd, uint32_t pat, uint32_t k) {
     const uint32_t *idx = flex + bd->o_idx;
     uint32_t e = flex[bd->o_rd + (k >> bd->rshift)];             // entry of rank (k >> rshift) << rshift: at or before k's
     uint32_t nxt = idx[e + 1u];
@@ -281,8 +306,8 @@ __device__ __forceinline__ int32_t ctx_fast(const uint32_t *ref2, const uint32_t
     if (pos + 1u < m || pos + m > ref_len) return -1;
     const uint32_t w0 = pos + 1u - m;                             // first base of the window
     const uint32_t wi = w0 >> 4, ei = w0 >> 5;
-    const uint32_t lo = ref2[wi], hi = ref2[wi + 1u];
-    const uint32_t elo = excm[ei], ehi = excm[ei + 1u];
+    const uint32_t lo = ldg32(ref2 + wi), hi = ldg32(ref2 + wi + 1u);
+    const uint32_t elo = ldg32(excm + ei), ehi = ldg32(excm + ei + 1u);
     const uint32_t W = __funnelshift_r(lo, hi, (w0 & 15u) * 2u);  // 16 bases from w0
     const uint32_t E = __funnelshift_r(elo, ehi, w0 & 31u);       // their exception bits
     const uint32_t m2 = (1u << (2u * m)) - 1u, m1 = (1u << m) - 1u;
@@ -324,7 +349,7 @@ __device__ __forceinline__ void w_add_cell(const DecodeParams &P, const WState &
     if (ins16 == 0u && outc < (uint32_t)P.n_code_slots && hslot >= 0) {
         const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
         const uint32_t within = (S.rev * (uint32_t)P.n_code_slots + outc) * (uint32_t)P.n_hap_slots + (uint32_t)hslot;
-        atomicAdd(&S.cells[(unsigned long long)(uint32_t)ref_pos * per_pos + within], 1ull | ((unsigned long long)is_mod << 32));
+        red_add_u64(S.cells + ((unsigned long long)(uint32_t)ref_pos * per_pos + within), 1ull | ((unsigned long long)is_mod << 32));
     } else {
         w_add_sparse(P, (uint32_t)S.tid, S.rev, ref_pos, outc, ins16, hap, is_mod);
     }
@@ -348,6 +373,8 @@ __device__ __forceinline__ void w_call_at(const DecodeParams &P, WRead *R, const
                                           const WBlock *bd, uint32_t blk_ord, uint32_t q, int32_t ref_pos, uint32_t ins_off,
                                           bool implicit, uint32_t cidx, uint32_t ml_base, uint32_t rd_code) {
     const WState &S = R->st;
+    const uint8_t *ml = S.ml;
+    const uint32_t *ref2 = S.ref2, *excm = S.excm;
     const uint32_t K = bd->K, is_n = bd->is_n;
     for (uint32_t m = 0; m < K; ++m) {
         const WCode cd = bd->code[m];
@@ -355,11 +382,11 @@ __device__ __forceinline__ void w_call_at(const DecodeParams &P, WRead *R, const
         uint32_t prob = 0, is_mod = 0;
         if (!implicit) {                                          // issued first: independent of the context test
             const unsigned long long ml_idx = (unsigned long long)ml_base + (unsigned long long)cidx * K + m;
-            if (ml_idx < S.ml_len) prob = S.ml[ml_idx]; else prob = 0x100u;
+            if (ml_idx < S.ml_len) prob = ldg8(ml + ml_idx); else prob = 0x100u;
         }
         if (cd.ctx_mode != kCtxNone) {                            // src/mod.c:1162-1172
             uint32_t refcode = 0;
-            int32_t in = cd.ctx_mode == kCtxFast ? ctx_fast(S.ref2, S.excm, S.ref_len, (uint32_t)ref_pos, cd.ctx_len, cd.pat2, refcode) : -1;
+            int32_t in = cd.ctx_mode == kCtxFast ? ctx_fast(ref2, excm, S.ref_len, (uint32_t)ref_pos, cd.ctx_len, cd.pat2, refcode) : -1;
             if (in < 0) {
                 if (!w_ctx_slow(P, S, (uint32_t)cd.ri, (uint32_t)ref_pos, q, is_n)) continue;
             } else {
@@ -367,7 +394,7 @@ __device__ __forceinline__ void w_call_at(const DecodeParams &P, WRead *R, const
                 if (!is_n) {                                      // ref->forward[pos] == read base
                     uint32_t rc = rd_code;
                     if (rc > 3u) {
-                        const uint32_t nib = (S.seq[q >> 1] >> ((~q & 1u) << 2)) & 0xfu;
+                        const uint32_t nib = (ldg8(S.seq + (q >> 1)) >> ((~q & 1u) << 2)) & 0xfu;
                         rc = nib == 1u ? 0u : nib == 2u ? 1u : nib == 4u ? 2u : nib == 8u ? 3u : 5u;
                     }
                     if (rc != refcode) continue;
@@ -393,14 +420,14 @@ __device__ __forceinline__ void w_call_at(const DecodeParams &P, WRead *R, const
 }
 
 // "base q of the read is a call" (SURVEY.md A.4): read position -> reference position, then the above
-__device__ __forceinline__ void w_call(const DecodeParams &P, WRead *R, const uint8_t *s_lut,
+__device__ __forceinline__ void w_call(const DecodeParams &P, WRead *R, const uint32_t *flex, const uint8_t *s_lut,
                                        const WBlock *bd, uint32_t blk_ord, uint32_t q, bool implicit, uint32_t cidx,
                                        uint32_t ml_base, uint32_t rd_code) {
     const WState &S = R->st;
-    AlnHit h = w_cigar_lookup(S, q);
+    AlnHit h = w_cigar_lookup(S, flex, q);
     int32_t ref_pos = h.aln;
     if (P.insertions && ref_pos < 0) {
-        if (implicit && S.rev) ref_pos = w_cigar_lookup(S, S.L - 1u - q).ins;          // Q9 (src/mod.c:1234,1314)
+        if (implicit && S.rev) ref_pos = w_cigar_lookup(S, flex, S.L - 1u - q).ins;    // Q9 (src/mod.c:1234,1314)
         else ref_pos = h.ins;
     }
     if (ref_pos < 0) return;                                      // src/mod.c:1127,1237,1317
@@ -706,10 +733,13 @@ __device__ __forceinline__ void w_count_entries(const WState &S, uint32_t *idx, 
 }
 
 // builds the index of block jb's class at (bd->o_idx, bd->o_rd) and fills bd->cnt_cls / bd->rshift
-__device__ __noinline__ void w_build_index(WRead *R, uint32_t jb, uint32_t lane) {
+__device__ __noinline__ void w_build_index(uint32_t aoff, uint32_t jb, uint32_t lane) {
+    const WArena A = w_arena(aoff);
+    WRead *R = A.R;
     WState &S = R->st;
     WBlock *bd = &R->blk[jb];
-    uint32_t *idx = S.flex + bd->o_idx, *rd = S.flex + bd->o_rd;
+    uint32_t *flex = A.flex;
+    uint32_t *idx = flex + bd->o_idx, *rd = flex + bd->o_rd;
     const uint32_t cls = bd->cls, n_ent = S.n_ent, pat = class_pat(cls);
     __syncwarp();
     if (cls == 0u) w_count_entries<true>(S, idx, pat, lane); else w_count_entries<false>(S, idx, pat, lane);
@@ -766,7 +796,7 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
     const uint32_t up = __shfl_up_sync(kFull, cm, 1);
     const uint32_t ncm = __shfl_down_sync(kFull, cm, 1);
     uint32_t pbit = (up >> 15) & 1u;
-    if (lane == 0) pbit = (tb > a0 && mm[tb - 1u] == ',') ? 1u : 0u;
+    if (lane == 0) pbit = (tb > a0 && ldg8(mm + tb - 1u) == ',') ? 1u : 0u;
     uint32_t st = ((cm << 1) | pbit) & ~cm & 0xffffu;              // token starts: previous byte is ','
     // clip to [a0, a1) and force a start at a0 (src/mod.c:1066: the list begins right after the header)
     uint32_t lo_b = a0 > p0 ? a0 - p0 : 0u, hi_b = a1 > p0 ? a1 - p0 : 0u;
@@ -825,6 +855,89 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
 }
 
 // ---------------------------------------------------------------------------------------
+// phase 4, common case in one tight loop: one requested code per block (K == 1), canonical base
+// C/G/T, `freq` without --insertions/--haplotypes, context "*" or <= 8 ACGT bases, un-sampled
+// CIGAR and index.  Same arithmetic as the staged passes below, no generality.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool w_fast_ok(const DecodeParams &P, const WState &S, const WBlock *bd) {
+    const WCode cd = bd->code[0];
+    return bd->K == 1 && cd.ri >= 0 && cd.ri < kWLutSlots && P.subtool == 1 && !P.insertions && !P.haplotypes &&
+           cd.ctx_mode != kCtxSlow && !bd->is_n && bd->cls != 0u && bd->cls != 4u && S.cshift == 0u && S.ishift == 0u &&
+           (uint32_t)cd.outc < (uint32_t)P.n_code_slots;
+}
+
+__device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *R, WTile *T, uint32_t *flex, const uint8_t *s_lut, const WBlock *bd,
+                                                  uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
+    const WState &S = R->st;
+    const uint32_t *idx = flex + bd->o_idx, *rd = flex + bd->o_rd, *dir = flex + S.o_dir, *cq = flex + S.o_cq, *cr = flex + S.o_cr;
+    uint32_t *bm = flex + bd->o_bm;
+    const uint32_t rshift = bd->rshift, cnt_cls = bd->cnt_cls, need_bm = bd->dot, cls = bd->cls, pat = class_pat(cls);
+    const uint32_t rev = S.rev, total_q = S.total_q, g = S.gshift, last_samp = S.n_samp - 1u, ml_len = S.ml_len, ref_len = S.ref_len;
+    const int32_t pos = S.pos;
+    const uint8_t *seq = S.seq, *ml = S.ml;
+    const uint32_t *ref2 = S.ref2, *excm = S.excm;
+    unsigned long long *cells = S.cells;
+    const WCode cd = bd->code[0];
+    const uint32_t m = cd.ctx_mode == kCtxFast ? cd.ctx_len : 0u, pat2 = cd.pat2;
+    const uint32_t m2 = (1u << (2u * m)) - 1u, m1 = (1u << m) - 1u;
+    const uint8_t *lut = s_lut + cd.ri * 256;
+    const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
+    const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
+    const uint32_t ml0 = ml_base + cidx0;
+    for (uint32_t c = lane; c < n; c += 32u) {
+        const uint32_t rank = T->rank[c];
+        if (rank >= cnt_cls) { w_raise(R, kErrMMRank); continue; }                  // src/mod.c:1116
+        const uint32_t mi = ml0 + c;
+        const uint32_t prob = mi < ml_len ? ldg8(ml + mi) : 0x100u;                // issued early
+        // ---- select: k-th base of the class
+        const uint32_t k = rev ? cnt_cls - 1u - rank : rank;
+        uint32_t e = rd[k >> rshift], nxt = idx[e + 1u];
+        while (nxt <= k) { ++e; nxt = idx[e + 1u]; }
+        uint32_t rem = k - idx[e];
+        const uint4 v = ld16(seq + (size_t)e * 16u);
+        const uint32_t f0 = nib_eq_flags(v.x, pat), f1 = nib_eq_flags(v.y, pat), f2 = nib_eq_flags(v.z, pat), f3 = nib_eq_flags(v.w, pat);
+        const uint32_t s0 = (uint32_t)__popc(f0), s1 = s0 + (uint32_t)__popc(f1), s2 = s1 + (uint32_t)__popc(f2);
+        uint32_t f = f0, wsel = 0, sub = 0;
+        if (rem >= s0) { f = f1; wsel = 8; sub = s0; }
+        if (rem >= s1) { f = f2; wsel = 16; sub = s1; }
+        if (rem >= s2) { f = f3; wsel = 24; sub = s2; }
+        rem -= sub;
+        uint32_t cc = (uint32_t)__popc(f & 0xffffu);
+        if (rem >= cc) { rem -= cc; f >>= 16; wsel += 4; }
+        cc = (uint32_t)__popc(f & 0xffu);
+        if (rem >= cc) { rem -= cc; f >>= 8; wsel += 2; }
+        const uint32_t q = e * 32u + wsel + ((rem != 0u || !(f & 0x80u)) ? 1u : 0u);
+        if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
+        // ---- map: aln[q]
+        if (q >= total_q) continue;
+        const uint32_t b = q >> g;
+        uint32_t lo = dir[b], hi = (((b + 1u) << g) < total_q) ? dir[b + 1u] : last_samp;
+        const uint32_t qlim = (q + 1u) << 4;
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (cq[mid] < qlim) lo = mid; else hi = mid - 1u; }
+        const uint32_t ce = cq[lo], op = ce & 15u;
+        if (op != 0u && op != 7u && op != 8u) continue;                             // src/mod.c:1127
+        const uint32_t ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
+        // ---- update
+        if (m) {
+            if (ref_pos + 1u < m || ref_pos + m > ref_len) {                        // contig edge: generic test
+                if (!w_ctx_slow(P, S, (uint32_t)cd.ri, ref_pos, q, 0u)) continue;
+            } else {
+                const uint32_t w0 = ref_pos + 1u - m, wi = w0 >> 4, ei = w0 >> 5;
+                const uint32_t W = __funnelshift_r(ldg32(ref2 + wi), ldg32(ref2 + wi + 1u), (w0 & 15u) * 2u);
+                const uint32_t E = __funnelshift_r(ldg32(excm + ei), ldg32(excm + ei + 1u), w0 & 31u);
+                uint32_t hit = 0;
+                for (uint32_t j = 0; j < m; ++j) hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
+                if (!hit || ((W >> (2u * (m - 1u))) & 3u) != cls) continue;         // src/mod.c:1162-1172
+            }
+        }
+        if (prob > 0xffu) { w_raise(R, kErrMLIndex); continue; }                    // src/mod.c:1174
+        const uint32_t fl = lut[prob];                                              // src/mod.c:1181-1191
+        if (!(fl & 1u)) continue;
+        red_add_u64(cells + ((unsigned long long)ref_pos * per_pos + within), 1ull | ((unsigned long long)((fl >> 1) & 1u) << 32));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // phase 4 (per text tile): the explicit calls whose ranks are in T->rank[0..n).  Three passes
 // staged through shared memory so that each is a short loop with independent iterations:
 //   select  base rank -> read position q            (bases_pos[][], src/mod.c:1102-1113)
@@ -834,48 +947,49 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
 constexpr uint32_t kNoCall = 0xffffffffu;
 
 template <bool C0>
-__device__ __forceinline__ void w_pass_select(WRead *R, WTile *T, const WBlock *bd, uint32_t pat, uint32_t n, uint32_t need_bm, uint32_t lane) {
+__device__ __forceinline__ void w_pass_select(WRead *R, WTile *T, uint32_t *flex, const WBlock *bd, uint32_t pat, uint32_t n, uint32_t need_bm, uint32_t lane) {
     const WState &S = R->st;
     const uint32_t rev = S.rev, cnt_cls = bd->cnt_cls;
-    uint32_t *bm = S.flex_home + bd->o_bm;
+    uint32_t *bm = flex + bd->o_bm;
     for (uint32_t c = lane; c < n; c += 32u) {
         const uint32_t r0 = T->rank[c];
         if (r0 >= cnt_cls) { w_raise(R, kErrMMRank); T->rank[c] = kNoCall; continue; }     // src/mod.c:1116
-        const SelProbe p0 = w_select_probe<C0>(S, bd, pat, rev ? cnt_cls - 1u - r0 : r0);
+        const SelProbe p0 = w_select_probe<C0>(S, flex, bd, pat, rev ? cnt_cls - 1u - r0 : r0);
         if (need_bm) atomicOr(&bm[r0 >> 5], 1u << (r0 & 31u));
         T->rank[c] = w_select_resolve<C0>(p0, pat);
     }
 }
 
-__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, uint32_t slot, uint32_t jb,
+__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WTile *T, uint32_t *flex, const uint8_t *s_lut, uint32_t slot, uint32_t jb,
                                              uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
     const WBlock *bd = &R->blk[slot];                              // jb: the block's ordinal in the read (view row order)
+    if (w_fast_ok(P, S, bd)) { w_tile_calls_fast(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); return; }
     const uint32_t cls = bd->cls, need_bm = bd->dot;
     const uint32_t pat = class_pat(cls), rd_code = cls >= 1u && cls <= 3u ? cls : 4u;
     // ---- select
     if (bd->is_n) {                                               // src/mod.c:1102-1107
         const uint32_t L = S.L, rev = S.rev;
-        uint32_t *bm = S.flex_home + bd->o_bm;
+        uint32_t *bm = flex + bd->o_bm;
         for (uint32_t c = lane; c < n; c += 32u) {
             const uint32_t rank = T->rank[c];
             if (rank >= L) { w_raise(R, kErrMMRank); T->rank[c] = kNoCall; continue; }
             if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
             T->rank[c] = rev ? L - 1u - rank : rank;
         }
-    } else if (cls == 0u) w_pass_select<true>(R, T, bd, pat, n, need_bm, lane);
-    else w_pass_select<false>(R, T, bd, pat, n, need_bm, lane);
+    } else if (cls == 0u) w_pass_select<true>(R, T, flex, bd, pat, n, need_bm, lane);
+    else w_pass_select<false>(R, T, flex, bd, pat, n, need_bm, lane);
     if (P.insertions) {                                           // ins[] fall-back and ins_offset: fused map + update
         for (uint32_t c = lane; c < n; c += 32u) {
             const uint32_t q = T->rank[c];
-            if (q != kNoCall) w_call(P, R, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
+            if (q != kNoCall) w_call(P, R, flex, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
         }
         return;
     }
     // ---- map
     for (uint32_t c = lane; c < n; c += 32u) {
         const uint32_t q = T->rank[c];
-        T->refp[c] = q != kNoCall ? w_cigar_lookup(S, q).aln : -1;
+        T->refp[c] = q != kNoCall ? w_cigar_lookup(S, flex, q).aln : -1;
     }
     // ---- update
     for (uint32_t c = lane; c < n; c += 32u) {
@@ -887,17 +1001,17 @@ __device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WT
 
 // implicit calls of a '.' block (src/mod.c:1203-1367): every base of the class whose rank is not
 // in the explicit-rank bitmap.  Needs bd->n_calls / last1 / ml_base.
-__device__ __forceinline__ void w_implicit_block(const DecodeParams &P, WRead *R, const uint8_t *s_lut, uint32_t jb, uint32_t lane) {
+__device__ __forceinline__ void w_implicit_block(const DecodeParams &P, WRead *R, const uint32_t *flex, const uint8_t *s_lut, uint32_t jb, uint32_t lane) {
     const WState &S = R->st;
     const WBlock *bd = &R->blk[jb];
-    const uint32_t *bm = S.flex_home + bd->o_bm, *idx = S.flex + bd->o_idx;
+    const uint32_t *bm = flex + bd->o_bm, *idx = flex + bd->o_idx;
     const uint32_t cnt_cls = bd->cnt_cls, ml_base = bd->ml_base;
     if (bd->is_n) {
         const uint32_t last1 = bd->n_calls > 0 ? bd->last1 : 0u;                    // last + 1
         const uint32_t bound = last1 > cnt_cls ? last1 : cnt_cls;                   // Q8
         for (uint32_t s = lane; s < bound; s += 32u) {
             if ((bm[s >> 5] >> (s & 31u)) & 1u) continue;
-            w_call(P, R, s_lut, bd, jb, S.rev ? S.L - 1u - s : s, true, s, ml_base, 4u);
+            w_call(P, R, flex, s_lut, bd, jb, S.rev ? S.L - 1u - s : s, true, s, ml_base, 4u);
         }
         return;
     }
@@ -917,7 +1031,7 @@ __device__ __forceinline__ void w_implicit_block(const DecodeParams &P, WRead *R
                     const uint32_t s = S.rev ? cnt_cls - 1u - fr : fr;
                     ++fr;
                     if ((bm[s >> 5] >> (s & 31u)) & 1u) continue;
-                    w_call(P, R, s_lut, bd, jb, b0 + t, true, s, ml_base, rd_code);
+                    w_call(P, R, flex, s_lut, bd, jb, b0 + t, true, s, ml_base, rd_code);
                 }
             }
         }
@@ -932,20 +1046,23 @@ __device__ __forceinline__ void w_stage_luts(const DecodeParams &P, uint8_t *s_l
 }
 
 // fused path: the non-inlined pieces of the block loop
-__device__ __noinline__ uint32_t w_fused_tile(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, uint32_t jb, uint32_t tb,
+__device__ __noinline__ uint32_t w_fused_tile(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t tb,
                                               uint32_t carry_cnt, uint32_t ml_base, uint32_t lane) {
+    const WArena A = w_arena(aoff);
+    WRead *R = A.R;
     WState &S = R->st;
     const WBlock *bd = &R->blk[jb];
     uint32_t sum = 0;
-    const uint32_t n = w_tile_ranks(R, T, tb, bd->hdr_end, bd->end, S.carry_sum, &sum, lane);
-    if (bd->any_req && n) w_tile_calls(P, R, T, s_lut, jb, jb, n, carry_cnt, ml_base, lane);
+    const uint32_t n = w_tile_ranks(R, A.T, tb, bd->hdr_end, bd->end, S.carry_sum, &sum, lane);
+    if (bd->any_req && n) w_tile_calls(P, R, A.T, A.flex, A.s_lut, jb, jb, n, carry_cnt, ml_base, lane);
     __syncwarp();
     if (lane == 0) S.carry_sum = sat_add(S.carry_sum, sum);
     __syncwarp();
     return n;
 }
-__device__ __noinline__ void w_fused_implicit(const DecodeParams &P, WRead *R, const uint8_t *s_lut, uint32_t jb, uint32_t lane) {
-    w_implicit_block(P, R, s_lut, jb, lane);
+__device__ __noinline__ void w_fused_implicit(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t lane) {
+    const WArena A = w_arena(aoff);
+    w_implicit_block(P, A.R, A.flex, A.s_lut, jb, lane);
 }
 
 // MINB = resident CTAs per SM the register allocation is bounded for (2: 128 regs, 3: 80, 4: 64);
@@ -958,15 +1075,12 @@ struct PreParams { const WRead *reads; uint32_t n; };
 template <int MINB, bool PRE>
 __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_constant__ DecodeParams P, const __grid_constant__ WarpParams W,
                                                                  const __grid_constant__ PreParams Q) {
-    MMC_DYN_SMEM(uint4, w_dyn);
-    uint8_t *s_lut = reinterpret_cast<uint8_t *>(w_dyn);
-    w_stage_luts(P, s_lut);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint8_t *arena = reinterpret_cast<uint8_t *>(w_dyn) + kWLutSlots * 256 + (size_t)warp * W.arena_bytes;
-    WFixed *wf = reinterpret_cast<WFixed *>(arena);
-    WRead *R = &wf->rd;
-    WTile *T = &wf->tl;
-    uint32_t *flex = reinterpret_cast<uint32_t *>(arena + sizeof(WFixed));
+    const uint32_t aoff = (uint32_t)kWLutSlots * 256u + warp * W.arena_bytes;
+    const WArena A = w_arena(aoff);
+    w_stage_luts(P, A.s_lut);
+    WRead *R = A.R;
+    uint32_t *flex = A.flex;
     const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
     WState &S = R->st;
     for (;;) {
@@ -1007,25 +1121,25 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
             const bool need_bm = w_needs_bitmap(bd);
             if (w_needs_index(bd)) {
                 if (S.cur_cls != cls) {
-                    w_build_index(R, jb, lane);
+                    w_build_index(aoff, jb, lane);
                     if (lane == 0) { S.cur_cls = cls; S.cur_blk = jb; }
                 } else if (lane == 0) { bd->cnt_cls = R->blk[S.cur_blk].cnt_cls; bd->rshift = R->blk[S.cur_blk].rshift; }
             }
             if (need_bm) {
                 const uint32_t words = ((S.L + 31u) >> 5) + 1u;
-                for (uint32_t w = lane; w < words; w += 32u) S.flex_home[bd->o_bm + w] = 0;
+                for (uint32_t w = lane; w < words; w += 32u) flex[bd->o_bm + w] = 0;
             }
             if (lane == 0) S.carry_sum = 0;
             __syncwarp();
             uint32_t carry_cnt = 0;
             for (uint32_t tb = a0 & ~15u; tb < a1; tb += (uint32_t)kWChunks * 16u)
-                carry_cnt += w_fused_tile(P, R, T, s_lut, jb, tb, carry_cnt, ml_base, lane);
+                carry_cnt += w_fused_tile(P, aoff, jb, tb, carry_cnt, ml_base, lane);
             err = w_err(R);
             if (err) break;
             if (lane == 0) { bd->n_calls = carry_cnt; bd->last1 = S.carry_sum; bd->ml_base = ml_base; }
             __syncwarp();
             if (need_bm) {
-                w_fused_implicit(P, R, s_lut, jb, lane);
+                w_fused_implicit(P, aoff, jb, lane);
                 err = w_err(R);
                 if (err) break;
             }

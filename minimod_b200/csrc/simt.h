@@ -15,7 +15,7 @@
 #define MMC_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
     ::cuda_emul::launch((grid), (block), [=]() { kernel(__VA_ARGS__); })
 // dynamic shared memory: one static buffer of the hardware maximum (CTAs run one after another)
-#define MMC_DYN_SMEM(type, name) static type name[(228 * 1024) / sizeof(type)] __attribute__((aligned(16)))
+#define MMC_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(::cuda_emul::g_dyn_smem)
 #else
 #include <cuda_runtime.h>
 #define MMC_LAUNCH(kernel, grid, block, stream, ...) \

@@ -31,6 +31,7 @@ static ucontext_t g_sched;
 static const std::function<void()> *g_body;
 static Fiber *g_running;
 Tls *g_cur;
+alignas(16) unsigned char g_dyn_smem[228 * 1024];
 static uint64_t g_xchg[8][2][32];        // [warp][generation parity][lane]
 static uint64_t g_pred[8][2];
 

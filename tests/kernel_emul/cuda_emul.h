@@ -35,6 +35,7 @@ struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned 
 namespace cuda_emul {
 struct Tls { uint3 threadIdx, blockIdx; dim3 blockDim, gridDim; };
 extern Tls *g_cur;                       // the fiber that is running
+extern unsigned char g_dyn_smem[228 * 1024];   // the (single) dynamic shared-memory array of the running CTA
 void launch(unsigned grid, unsigned block, const std::function<void()> &body);
 void sync_block();
 uint64_t warp_exchange(uint64_t v, int src_lane_or_neg);   // value held by src lane (own if out of range)
@@ -65,6 +66,7 @@ static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int m) {
 }
 static inline unsigned __ballot_sync(unsigned, int pred) { return ::cuda_emul::warp_ballot(pred != 0); }
 
+template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
