@@ -455,24 +455,31 @@ __device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, WRead *R,
     WBlock &bd = R->blk[blk];
     const uint32_t start = blk == 0 ? 0u : R->semi[blk - 1u] + 1u;
     const uint32_t end = blk < S.n_semi ? R->semi[blk] : S.mm_len;
-    const uint8_t *mm = S.mm;
+    const uint8_t *mmg = S.mm;
+    // the header is a handful of characters: fetch 48 bytes around it at once, parse from the copy
+    const uint32_t w0 = start & ~15u;
+    uint4 win[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) win[k] = w0 + 16u * k < S.mm_len ? ld16(mmg + w0 + 16u * k) : make_uint4(0, 0, 0, 0);
+    const uint8_t *wb = reinterpret_cast<const uint8_t *>(win);
+    auto at = [&](uint32_t i) -> uint32_t { return i - w0 < 48u ? (uint32_t)wb[i - w0] : ldg8(mmg + i); };
     bd.end = end; bd.hdr_end = end; bd.K = 0; bd.any_req = 0; bd.cls = 0; bd.is_n = 0; bd.dot = 1;
     bd.o_idx = 0; bd.o_rd = 0; bd.rshift = 0; bd.cnt_cls = 0; bd.o_bm = 0; bd.n_calls = 0; bd.last1 = 0; bd.ml_base = 0; bd.tile0 = 0; bd.n_tiles = 0;
     for (int k = 0; k < kMaxCodes; ++k) { WCode c; c.ri = -1; c.outc = 0; c.ctx_mode = kCtxNone; c.ctx_len = 0; c.pat2 = 0; bd.code[k] = c; }
     uint32_t i = start;
-    const uint32_t base_c = i < end ? mm[i] : 0u;
+    const uint32_t base_c = i < end ? at(i) : 0u;
     const bool okb = base_c == 'A' || base_c == 'C' || base_c == 'G' || base_c == 'T' || base_c == 'U' || base_c == 'N' ||
                      base_c == 'a' || base_c == 'c' || base_c == 'g' || base_c == 't' || base_c == 'u' || base_c == 'n';
     if (!okb) return kErrMMBase;
     ++i;
     const uint32_t modbase = base_c == 'U' ? (uint32_t)'T' : base_c;                 // src/mod.c:1006
-    const uint32_t strand_c = i < end ? mm[i] : 0u;
+    const uint32_t strand_c = i < end ? at(i) : 0u;
     if (strand_c != '+' && strand_c != '-') return kErrMMStrand;
     ++i;
     unsigned long long codes = 0;                                                    // up to 8 code characters
     uint32_t j = 0; bool has_num = false, has_alpha = false, bad = false, too_many = false;
     while (i < end) {
-        const uint32_t c = mm[i];
+        const uint32_t c = at(i);
         if (c == ',' || c == '?' || c == '.') break;
         if (c >= '0' && c <= '9') has_num = true;
         else if ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) has_alpha = true;
@@ -483,7 +490,7 @@ __device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, WRead *R,
     if (bad || j == 0 || (has_num && has_alpha)) return kErrMMCode;
     if (too_many) return kErrTooManyCodes;
     const uint32_t K = has_num ? 1u : j;                                             // src/mod.c:1048
-    if (i < end && (mm[i] == '?' || mm[i] == '.')) { bd.dot = mm[i] == '.'; ++i; }
+    if (i < end && (at(i) == '?' || at(i) == '.')) { bd.dot = at(i) == '.'; ++i; }
     bd.hdr_end = i;
     bd.K = (uint8_t)K;
     uint32_t mb = modbase;                                                           // src/mod.c:1092-1093, table :98
@@ -842,9 +849,9 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
                 val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
             }
             if (bad) { w_raise(R, kErrMMSkip); val = 0; }
-            x = val + 1u;
+            x = val + 1u < kWMaxL ? val + 1u : kWMaxL;             // >= 2^26 is past any read this path takes; 32 of them fit 32 bits
         }
-        const uint32_t si = warp_incl_scan_sat(x, lane);
+        const uint32_t si = warp_incl_scan(x, lane);
         if (c < tile_cnt) T->rank[c] = sat_add(carry, si) - 1u;   // base_rank (src/mod.c:1098)
         const uint32_t rt = __shfl_sync(kFull, si, 31);
         carry = sat_add(carry, rt); total = sat_add(total, rt);
