@@ -326,10 +326,10 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         PreParams Q; Q.reads = nullptr; Q.n = 0;
         if (ctx->split_path) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
-            F.fa.arena_words = (ctx->w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
+            F.arena_bytes = ctx->w_arena_bytes;
             F.read_count = n;
             const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
-            MMC_LAUNCH(k_flat_setup, rgrid, (unsigned)kFThreads, s.stream, P, F);
+            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, wsmem, s.stream, P, F);
             CU(ctx, cudaGetLastError());
             ctx->tm.kernel_launches += 1;
             Q.reads = s.d_reads; Q.n = n;
@@ -460,6 +460,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         do {                                                                                                                     \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+            CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, (k_decode_warp<MB, true>), kWThreads, smem));               \
         } while (0)
         if (ctx->w_minb == 2) MMC_WARP_ATTR(2); else if (ctx->w_minb == 3) MMC_WARP_ATTR(3); else MMC_WARP_ATTR(4);

@@ -25,20 +25,40 @@ constexpr int kFThreads = 256;               // 8 warps per CTA
 
 struct FlatParams {
     WRead *reads;                            // [n_reads]: state + block table of every read, in HBM
-    FlatAlloc fa;                            // pool for the CIGAR arrays (dir | cq | cr) + the consumer's arena size
+    FlatAlloc fa;                            // pool for the CIGAR arrays (dir | cq | cr)
     uint32_t *defer_list, *defer_n;          // reads left to k_decode_warp<!PRE>
     uint32_t read_count;
+    uint32_t arena_bytes;                    // per warp: the same arena as the consumer kernel, so the layouts agree
 };
 
 __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t aoff = (uint32_t)kWLutSlots * 256u + warp * F.arena_bytes;
+    const WArena A = w_arena(aoff);
+    const uint32_t flex_words = (F.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < F.read_count; r += n_warps) {
-        WRead *R = &F.reads[r];
+        WRead *G = &F.reads[r];
         __syncwarp();
-        const bool ok = w_setup_read(P, R, nullptr, 0u, &F.fa, F.defer_list, F.defer_n, r, lane);
+        bool ok = w_setup_read(P, aoff, flex_words, F.defer_list, F.defer_n, r, lane);
         __syncwarp();
-        if (!ok && lane == 0) R->st.n_blocks = 0;                           // not ours (or fatal): the consumer skips it
+        unsigned long long base = 0;
+        const uint32_t take = ok ? A.R->st.n_stage : 0u;
+        if (ok) {                                                           // CIGAR arrays -> pool
+            if (lane == 0) base = atomicAdd(F.fa.cursor, (unsigned long long)take);
+            base = ((unsigned long long)__shfl_sync(kFull, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)base, 0);
+            if (base + take > F.fa.cap) { w_defer(F.defer_list, F.defer_n, r, lane); ok = false; }
+        }
+        if (!ok) { if (lane == 0) G->st.n_blocks = 0; continue; }           // not ours (or fatal): the consumer skips it
+        uint4 *d4 = reinterpret_cast<uint4 *>(F.fa.pool + base);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(A.flex);
+        for (uint32_t i = lane; i < (take >> 2); i += 32u) d4[i] = s4[i];
+        const uint32_t words = (uint32_t)((sizeof(WState) + sizeof(uint32_t) * (kWBlocks + 4) + sizeof(WBlock) * A.R->st.n_blocks) / 4);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.R);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(G);
+        for (uint32_t i = lane; i < words; i += 32u) dst[i] = src[i];
+        __syncwarp();
+        if (lane == 0) { G->st.flex = F.fa.pool + base; G->st.flex_home = F.fa.pool + base; }
     }
 }
 

@@ -118,12 +118,10 @@ struct WarpParams {
     uint32_t *defer_n;
 };
 
-struct FlatAlloc {                           // flat path: bump allocator over a global scratch pool (words)
+struct FlatAlloc {                           // split path: bump allocator over a global scratch pool (words)
     uint32_t *pool;
     unsigned long long *cursor;
     unsigned long long cap;
-    uint32_t arena_words;                    // != 0: "split" mode -- only dir|cq|cr go to the pool, the index and the
-                                             // bitmap are laid out for a shared-memory arena of that many words
 };
 
 // ---------------------------------------------------------------------------------------
@@ -450,7 +448,8 @@ __device__ __forceinline__ void w_report(const DecodeParams &P, uint32_t r, uint
 }
 
 // one MM block header (src/mod.c:1003-1062); same rules as k_decode's (2b).  Returns an error code.
-__device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, WRead *R, uint32_t blk) {
+__device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, uint32_t aoff, uint32_t blk) {
+    WRead *R = w_arena(aoff).R;
     const WState &S = R->st;
     WBlock &bd = R->blk[blk];
     const uint32_t start = blk == 0 ? 0u : R->semi[blk - 1u] + 1u;
@@ -540,8 +539,11 @@ __device__ __forceinline__ bool w_needs_bitmap(const WBlock *bd) { return bd->an
 //   flat path:  the scratch comes from the global pool `fa`; one index per distinct class and one
 //               bitmap per '.' block, so that later kernels can work on any block / tile independently
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint32_t *flex, uint32_t flex_words, const FlatAlloc *fa,
+__device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, uint32_t flex_words,
                                           uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane) {
+    const WArena A = w_arena(aoff);
+    WRead *R = A.R;
+    uint32_t *flex = A.flex;
     WState &S = R->st;
     const int32_t tid = P.tid[r];
     const uint32_t L = P.l_seq[r], n_cig = P.n_cigar[r], mm_len = P.mm_len[r];
@@ -590,7 +592,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
     // ---- block headers, one lane each
     uint32_t herr = kErrNone, my_idx = 0, my_bm = 0, my_cls = 0;
     if (lane < n_blocks) {
-        herr = w_parse_header(P, R, lane);
+        herr = w_parse_header(P, aoff, lane);
         if (herr == kErrNone) { my_idx = w_needs_index(&R->blk[lane]); my_bm = w_needs_bitmap(&R->blk[lane]); my_cls = R->blk[lane].cls; }
     }
     const uint32_t herr_mask = __ballot_sync(kFull, herr != kErrNone);
@@ -609,10 +611,9 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
     const uint32_t n_dir = (L >> gshift) + 2u;
     const uint32_t n_rd = (L >> 5) + 2u;
     const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
-    const bool per_block = fa && fa->arena_words == 0u;                              // flat: one index per class, one bitmap per block
-    const uint32_t n_idx = per_block ? (uint32_t)__popc(cls_set) : (idx_mask ? 1u : 0u);
-    const uint32_t n_bm = per_block ? (uint32_t)__popc(bm_mask) : (bm_mask ? 1u : 0u);
-    const uint32_t cap = per_block ? (1u << 20) : fa ? fa->arena_words : flex_words; // flat: sample only absurdly large reads
+    const uint32_t n_idx = idx_mask ? 1u : 0u, n_bm = bm_mask ? 1u : 0u;             // one index / bitmap, reused block after block
+    const uint32_t cap = flex_words;
+    (void)cls_set;
     uint32_t cshift = 0, ishift = 0, n_samp, n_ent, need;
     auto a4 = [](uint32_t x) { return (x + 3u) & ~3u; };
     for (;;) {
@@ -625,37 +626,24 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, WRead *R, uint3
         if ((2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
         else ++ishift;
     }
-    if (fa) {                                                                        // bump-allocate from the global pool
-        const uint32_t take = per_block ? need : a4(n_dir + 2u * n_samp);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(fa->cursor, (unsigned long long)take);
-        base = ((unsigned long long)__shfl_sync(kFull, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)base, 0);
-        if (base + take > fa->cap) { w_defer(defer_list, defer_n, r, lane); return false; }
-        flex = fa->pool + base;
-    }
     const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = a4(o_cr + n_samp);
     if (lane == 0) {
         S.flex = flex; S.flex_home = flex;
         S.o_dir = o_dir; S.o_cq = o_cq; S.o_cr = o_cr;
         S.cshift = cshift; S.gshift = gshift; S.ishift = ishift; S.n_samp = n_samp; S.n_ent = n_ent; S.n_u4 = n_u4; S.n_rd = n_rd;
         // per block: where its class index / bitmap live
-        uint32_t cls_off[5] = {0, 0, 0, 0, 0}, next = o_var, seen = 0;
+        uint32_t next = o_var;
         for (uint32_t b = 0; b < n_blocks; ++b) {
             WBlock &bd = R->blk[b];
             if ((idx_mask >> b) & 1u) {
-                const uint32_t c = bd.cls;
-                if (!per_block) { bd.o_idx = o_var; bd.o_rd = o_var + n_ent + 2u; }
-                else {
-                    if (!((seen >> c) & 1u)) { cls_off[c] = next; next += a4(n_ent + 2u + n_rd); seen |= 1u << c; }
-                    bd.o_idx = cls_off[c]; bd.o_rd = cls_off[c] + n_ent + 2u;
-                }
+                bd.o_idx = o_var; bd.o_rd = o_var + n_ent + 2u;
             }
         }
-        if (!per_block) next = o_var + n_idx * a4(n_ent + 2u + n_rd);
-        S.n_stage = per_block ? next : o_var;
+        next = o_var + n_idx * a4(n_ent + 2u + n_rd);
+        S.n_stage = o_var;                                         // dir | cq | cr: what k_flat_setup hands over
         for (uint32_t b = 0; b < n_blocks; ++b) {
             WBlock &bd = R->blk[b];
-            if ((bm_mask >> b) & 1u) { bd.o_bm = next; if (per_block) next += a4(bm_words); }
+            if ((bm_mask >> b) & 1u) bd.o_bm = next;
         }
     }
 
@@ -761,7 +749,7 @@ __device__ __noinline__ void w_build_index(uint32_t aoff, uint32_t jb, uint32_t 
     const uint32_t total = __shfl_sync(kFull, incl, 31);
     uint32_t run = incl - sum;
     for (uint32_t e = e0; e < e1; ++e) { const uint32_t c = idx[e]; idx[e] = run; run += c; }
-    uint32_t rshift = 2;
+    uint32_t rshift = 4;
     while (((total >> rshift) + 1u) > S.n_rd) ++rshift;
     if (lane == 0) { idx[n_ent] = total; bd->cnt_cls = total; bd->rshift = rshift; }
     __syncwarp();
@@ -1116,7 +1104,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
             __syncwarp();
         } else {
             if (r >= P.n_reads) break;
-            if (!w_setup_read(P, R, flex, flex_words, nullptr, W.defer_list, W.defer_n, r, lane)) continue;
+            if (!w_setup_read(P, aoff, flex_words, W.defer_list, W.defer_n, r, lane)) continue;
         }
 
         // ---- blocks in order
