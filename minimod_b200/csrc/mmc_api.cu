@@ -77,6 +77,7 @@ struct mmc_ctx {
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
+    uint32_t setup_arena_bytes = kWReadBytes + 4608;   // k_flat_setup: WRead + 1152 words for dir | cq | cr
     int w_minb = 3;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
     uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
     int n_code_slots = 1, n_hap_slots = 1, wild_req = -1;
@@ -326,10 +327,11 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         PreParams Q; Q.reads = nullptr; Q.n = 0;
         if (ctx->split_path) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
-            F.arena_bytes = ctx->w_arena_bytes;
+            F.arena_bytes = ctx->setup_arena_bytes;
+            F.consumer_flex_words = (ctx->w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
             F.read_count = n;
             const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
-            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, wsmem, s.stream, P, F);
+            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWLutSlots * 256 + (size_t)ctx->setup_arena_bytes * (kFThreads / 32), s.stream, P, F);
             CU(ctx, cudaGetLastError());
             ctx->tm.kernel_launches += 1;
             Q.reads = s.d_reads; Q.n = n;
@@ -460,7 +462,8 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         do {                                                                                                                     \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+            CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize,                                  \
+                                     (int)((size_t)kWLutSlots * 256 + (size_t)ctx->setup_arena_bytes * (kFThreads / 32))));      \
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, (k_decode_warp<MB, true>), kWThreads, smem));               \
         } while (0)
         if (ctx->w_minb == 2) MMC_WARP_ATTR(2); else if (ctx->w_minb == 3) MMC_WARP_ATTR(3); else MMC_WARP_ATTR(4);

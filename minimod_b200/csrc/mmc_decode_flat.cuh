@@ -28,19 +28,20 @@ struct FlatParams {
     FlatAlloc fa;                            // pool for the CIGAR arrays (dir | cq | cr)
     uint32_t *defer_list, *defer_n;          // reads left to k_decode_warp<!PRE>
     uint32_t read_count;
-    uint32_t arena_bytes;                    // per warp: the same arena as the consumer kernel, so the layouts agree
+    uint32_t arena_bytes;                    // per warp, this kernel: WRead + room for dir | cq | cr
+    uint32_t consumer_flex_words;            // flex capacity of the consumer's arena: decides the sampling shifts
 };
 
 __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t aoff = (uint32_t)kWLutSlots * 256u + warp * F.arena_bytes;
-    const WArena A = w_arena(aoff);
-    const uint32_t flex_words = (F.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
+    const WArena A = w_arena<false>(aoff);
+    const uint32_t local_words = (F.arena_bytes - kWReadBytes) / 4u;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < F.read_count; r += n_warps) {
         WRead *G = &F.reads[r];
         __syncwarp();
-        bool ok = w_setup_read(P, aoff, flex_words, F.defer_list, F.defer_n, r, lane);
+        bool ok = w_setup_read<false>(P, aoff, F.consumer_flex_words, local_words, F.defer_list, F.defer_n, r, lane);
         __syncwarp();
         unsigned long long base = 0;
         const uint32_t take = ok ? A.R->st.n_stage : 0u;

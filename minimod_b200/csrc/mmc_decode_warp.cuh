@@ -100,7 +100,10 @@ struct WFixed {                              // fixed part of a warp's arena on 
     WTile tl;
 };
 
+// TILE = false: an arena without the WTile part (k_flat_setup): flex follows WRead directly.
 struct WArena { uint8_t *s_lut; WRead *R; WTile *T; uint32_t *flex; };
+constexpr uint32_t kWReadBytes = (uint32_t)((sizeof(WRead) + 15) / 16 * 16);
+template <bool TILE = true>
 __device__ __forceinline__ WArena w_arena(uint32_t aoff) {
     MMC_DYN_SMEM(uint4, w_dyn);
     uint8_t *base = reinterpret_cast<uint8_t *>(w_dyn);
@@ -108,7 +111,7 @@ __device__ __forceinline__ WArena w_arena(uint32_t aoff) {
     A.s_lut = base;
     WFixed *wf = reinterpret_cast<WFixed *>(base + aoff);
     A.R = &wf->rd; A.T = &wf->tl;
-    A.flex = reinterpret_cast<uint32_t *>(base + aoff + sizeof(WFixed));
+    A.flex = reinterpret_cast<uint32_t *>(base + aoff + (TILE ? (uint32_t)sizeof(WFixed) : kWReadBytes));
     return A;
 }
 
@@ -448,8 +451,9 @@ __device__ __forceinline__ void w_report(const DecodeParams &P, uint32_t r, uint
 }
 
 // one MM block header (src/mod.c:1003-1062); same rules as k_decode's (2b).  Returns an error code.
+template <bool TILE>
 __device__ __noinline__ uint32_t w_parse_header(const DecodeParams &P, uint32_t aoff, uint32_t blk) {
-    WRead *R = w_arena(aoff).R;
+    WRead *R = w_arena<TILE>(aoff).R;
     const WState &S = R->st;
     WBlock &bd = R->blk[blk];
     const uint32_t start = blk == 0 ? 0u : R->semi[blk - 1u] + 1u;
@@ -539,9 +543,12 @@ __device__ __forceinline__ bool w_needs_bitmap(const WBlock *bd) { return bd->an
 //   flat path:  the scratch comes from the global pool `fa`; one index per distinct class and one
 //               bitmap per '.' block, so that later kernels can work on any block / tile independently
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, uint32_t flex_words,
+//   flex_words   capacity of the arena that will hold dir|cq|cr + index + bitmap (decides the sampling shifts)
+//   local_words  capacity of THIS arena for dir|cq|cr (k_flat_setup's arenas are smaller than the consumer's)
+template <bool TILE>
+__device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, uint32_t flex_words, uint32_t local_words,
                                           uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane) {
-    const WArena A = w_arena(aoff);
+    const WArena A = w_arena<TILE>(aoff);
     WRead *R = A.R;
     uint32_t *flex = A.flex;
     WState &S = R->st;
@@ -592,7 +599,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     // ---- block headers, one lane each
     uint32_t herr = kErrNone, my_idx = 0, my_bm = 0, my_cls = 0;
     if (lane < n_blocks) {
-        herr = w_parse_header(P, aoff, lane);
+        herr = w_parse_header<TILE>(P, aoff, lane);
         if (herr == kErrNone) { my_idx = w_needs_index(&R->blk[lane]); my_bm = w_needs_bitmap(&R->blk[lane]); my_cls = R->blk[lane].cls; }
     }
     const uint32_t herr_mask = __ballot_sync(kFull, herr != kErrNone);
@@ -621,7 +628,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
         if (n_samp == 0u) n_samp = 1u;
         n_ent = (n_u4 + (1u << ishift) - 1u) >> ishift;
         need = a4(n_dir + 2u * n_samp) + n_idx * a4(n_ent + 2u + n_rd) + n_bm * a4(bm_words);   // 16-byte aligned pieces
-        if (need <= cap) break;
+        if (need <= cap && a4(n_dir + 2u * n_samp) <= local_words) break;
         if (cshift >= (uint32_t)kWMaxCShift && ishift >= (uint32_t)kWMaxIShift) { w_defer(defer_list, defer_n, r, lane); return false; }
         if ((2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
         else ++ishift;
@@ -1104,7 +1111,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
             __syncwarp();
         } else {
             if (r >= P.n_reads) break;
-            if (!w_setup_read(P, aoff, flex_words, W.defer_list, W.defer_n, r, lane)) continue;
+            if (!w_setup_read<true>(P, aoff, flex_words, flex_words, W.defer_list, W.defer_n, r, lane)) continue;
         }
 
         // ---- blocks in order
