@@ -94,6 +94,13 @@ struct mmc_ctx {
     // ref-pack staging
     uint8_t *d_ascii = nullptr; size_t ascii_cap = 0;
     uint32_t *d_exc_tmp_start = nullptr; uint8_t *d_exc_tmp_letter = nullptr; uint32_t *d_exc_n = nullptr;
+    // finalize scratch, grown on demand and kept: tile counts / offsets / totals, device rows, pinned host rows
+    uint32_t *d_tile_count = nullptr; unsigned long long *d_tile_off = nullptr, *d_totals = nullptr;
+    size_t fin_tiles_cap = 0, fin_jobs_cap = 0;
+    FreqRecDev *d_rows = nullptr; size_t d_rows_cap = 0;
+    mmc_freq_rec_t *h_rows = nullptr; size_t h_rows_cap = 0;       // pinned
+    unsigned long long *h_totals = nullptr;                        // pinned, fin_jobs_cap entries
+    cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
     // results
     std::vector<mmc_freq_rec_t> freq_out;
     std::vector<std::string> code_names;
@@ -534,6 +541,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     ctx->view_cap = o.view_capacity ? o.view_capacity : std::max<uint64_t>(1u << 16, o.max_bytes);
     CUC(cudaStreamCreateWithFlags(&ctx->fin_stream, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&ctx->ev_f0)); CUC(cudaEventCreate(&ctx->ev_f1));
+    CUC(cudaEventCreate(&ctx->ev_d0)); CUC(cudaEventCreate(&ctx->ev_d1));
 
     ctx->slots.resize(o.n_slots);
     for (Slot &s : ctx->slots) {
@@ -589,6 +597,14 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (ctx->d_exc_tmp_start) cudaFree(ctx->d_exc_tmp_start);
     if (ctx->d_exc_tmp_letter) cudaFree(ctx->d_exc_tmp_letter);
     if (ctx->d_exc_n) cudaFree(ctx->d_exc_n);
+    if (ctx->d_tile_count) cudaFree(ctx->d_tile_count);
+    if (ctx->d_tile_off) cudaFree(ctx->d_tile_off);
+    if (ctx->d_totals) cudaFree(ctx->d_totals);
+    if (ctx->d_rows) cudaFree(ctx->d_rows);
+    if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->ev_d0) cudaEventDestroy(ctx->ev_d0);
+    if (ctx->ev_d1) cudaEventDestroy(ctx->ev_d1);
     if (ctx->ev_f0) cudaEventDestroy(ctx->ev_f0);
     if (ctx->ev_f1) cudaEventDestroy(ctx->ev_f1);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
@@ -803,14 +819,25 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
         tiles += j.n_tiles;
         jobs.push_back(j);
     }
-    std::vector<mmc_freq_rec_t> dense;
-    uint32_t *d_tile_count = nullptr; unsigned long long *d_tile_off = nullptr, *d_totals = nullptr;
-    FreqRecDev *d_out = nullptr;
+    uint64_t n_dense = 0;
     CU(ctx, cudaEventRecord(ctx->ev_f0, ctx->fin_stream));
     if (tiles) {
-        CU(ctx, cudaMalloc((void **)&d_tile_count, 4 * tiles));
-        CU(ctx, cudaMalloc((void **)&d_tile_off, 8 * tiles));
-        CU(ctx, cudaMalloc((void **)&d_totals, 8 * jobs.size()));
+        if (tiles > ctx->fin_tiles_cap) {
+            if (ctx->d_tile_count) cudaFree(ctx->d_tile_count);
+            if (ctx->d_tile_off) cudaFree(ctx->d_tile_off);
+            ctx->d_tile_count = nullptr; ctx->d_tile_off = nullptr; ctx->fin_tiles_cap = 0;
+            CU(ctx, cudaMalloc((void **)&ctx->d_tile_count, 4 * tiles));
+            CU(ctx, cudaMalloc((void **)&ctx->d_tile_off, 8 * tiles));
+            ctx->fin_tiles_cap = tiles;
+        }
+        if (jobs.size() > ctx->fin_jobs_cap) {
+            if (ctx->d_totals) cudaFree(ctx->d_totals);
+            if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+            ctx->d_totals = nullptr; ctx->h_totals = nullptr; ctx->fin_jobs_cap = 0;
+            CU(ctx, cudaMalloc((void **)&ctx->d_totals, 8 * jobs.size()));
+            CU(ctx, cudaMallocHost((void **)&ctx->h_totals, 8 * jobs.size()));
+            ctx->fin_jobs_cap = jobs.size();
+        }
         std::vector<FinalizeParams> fps(jobs.size());
         for (size_t k = 0; k < jobs.size(); ++k) {
             const Job &j = jobs[k];
@@ -819,33 +846,47 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             fp.cells = ctx->contigs[j.tid].dev.cells + (uint64_t)j.lo * spp;
             fp.n_cells = j.n_cells; fp.tid = j.tid; fp.lo = j.lo;
             fp.n_code_slots = ctx->n_code_slots; fp.n_hap_slots = ctx->n_hap_slots; fp.haplotypes = ctx->opts.haplotypes;
-            fp.tile_count = d_tile_count + j.tile0; fp.tile_offset = d_tile_off + j.tile0; fp.cells_per_tile = kTileCells;
+            fp.tile_count = ctx->d_tile_count + j.tile0; fp.tile_offset = ctx->d_tile_off + j.tile0; fp.cells_per_tile = kTileCells;
             MMC_LAUNCH(k_count_nonzero, (unsigned)j.n_tiles, 256u, ctx->fin_stream, fp);
             CU(ctx, cudaGetLastError());
-            MMC_LAUNCH(k_scan_tiles, 1u, 256u, ctx->fin_stream, fp.tile_count, fp.tile_offset, (uint32_t)j.n_tiles, d_totals + k);
+            MMC_LAUNCH(k_scan_tiles, 1u, 256u, ctx->fin_stream, fp.tile_count, fp.tile_offset, (uint32_t)j.n_tiles, ctx->d_totals + k);
             CU(ctx, cudaGetLastError());
             ctx->tm.kernel_launches += 2;
         }
-        std::vector<unsigned long long> totals(jobs.size());
-        CU(ctx, cudaMemcpyAsync(totals.data(), d_totals, 8 * jobs.size(), cudaMemcpyDeviceToHost, ctx->fin_stream));
+        CU(ctx, cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 8 * jobs.size(), cudaMemcpyDeviceToHost, ctx->fin_stream));
         CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
         uint64_t total = 0;
-        for (unsigned long long t : totals) total += t;
+        for (size_t k = 0; k < jobs.size(); ++k) total += ctx->h_totals[k];
         if (total) {
-            CU(ctx, cudaMalloc((void **)&d_out, sizeof(FreqRecDev) * total));
+            if (total > ctx->d_rows_cap) {
+                if (ctx->d_rows) cudaFree(ctx->d_rows);
+                ctx->d_rows = nullptr; ctx->d_rows_cap = 0;
+                const size_t cap = total + total / 8 + 1024;
+                CU(ctx, cudaMalloc((void **)&ctx->d_rows, sizeof(FreqRecDev) * cap));
+                ctx->d_rows_cap = cap;
+            }
+            if (total > ctx->h_rows_cap) {
+                if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
+                ctx->h_rows = nullptr; ctx->h_rows_cap = 0;
+                const size_t cap = total + total / 8 + 1024;
+                CU(ctx, cudaMallocHost((void **)&ctx->h_rows, sizeof(mmc_freq_rec_t) * cap));
+                ctx->h_rows_cap = cap;
+            }
             uint64_t base = 0;
             for (size_t k = 0; k < jobs.size(); ++k) {
-                if (!totals[k]) continue;
-                fps[k].out = d_out; fps[k].out_base = base;
+                if (!ctx->h_totals[k]) continue;
+                fps[k].out = ctx->d_rows; fps[k].out_base = base;
                 MMC_LAUNCH(k_emit_records, (unsigned)jobs[k].n_tiles, 256u, ctx->fin_stream, fps[k]);
                 CU(ctx, cudaGetLastError());
                 ctx->tm.kernel_launches += 1;
-                base += totals[k];
+                base += ctx->h_totals[k];
             }
-            dense.resize(total);
             CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
-            CU(ctx, cudaMemcpyAsync(dense.data(), d_out, sizeof(FreqRecDev) * total, cudaMemcpyDeviceToHost, ctx->fin_stream));
+            CU(ctx, cudaEventRecord(ctx->ev_d0, ctx->fin_stream));
+            CU(ctx, cudaMemcpyAsync(ctx->h_rows, ctx->d_rows, sizeof(FreqRecDev) * total, cudaMemcpyDeviceToHost, ctx->fin_stream));
+            CU(ctx, cudaEventRecord(ctx->ev_d1, ctx->fin_stream));
             ctx->tm.d2h_bytes += sizeof(FreqRecDev) * total;
+            n_dense = total;
         } else {
             CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
         }
@@ -856,11 +897,8 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
     {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev_f0, ctx->ev_f1) == cudaSuccess) ctx->tm.finalize_ms += ms;
+        if (n_dense && cudaEventElapsedTime(&ms, ctx->ev_d0, ctx->ev_d1) == cudaSuccess) ctx->tm.d2h_ms += ms;
     }
-    if (d_tile_count) cudaFree(d_tile_count);
-    if (d_tile_off) cudaFree(d_tile_off);
-    if (d_totals) cudaFree(d_totals);
-    if (d_out) cudaFree(d_out);
 
     // ---- sparse side buffer: sort + reduce on the host, then merge with the dense rows
     unsigned long long sn = 0;
@@ -907,11 +945,17 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
         if (x.ins_offset != y.ins_offset) return x.ins_offset < y.ins_offset;
         return x.hap < y.hap;
     };
-    ctx->freq_out.clear();
-    ctx->freq_out.resize(dense.size() + sparse.size());
-    std::merge(dense.begin(), dense.end(), sparse.begin(), sparse.end(), ctx->freq_out.begin(), less);
-    *recs = ctx->freq_out.data();
-    *n_recs = ctx->freq_out.size();
+    if (sparse.empty()) {                                    // the pinned rows are the result as they are
+        ctx->freq_out.clear();
+        *recs = n_dense ? ctx->h_rows : nullptr;
+        *n_recs = n_dense;
+    } else {
+        ctx->freq_out.clear();
+        ctx->freq_out.resize(n_dense + sparse.size());
+        std::merge(ctx->h_rows, ctx->h_rows + n_dense, sparse.begin(), sparse.end(), ctx->freq_out.begin(), less);
+        *recs = ctx->freq_out.data();
+        *n_recs = ctx->freq_out.size();
+    }
     return MMC_OK;
 }
 
