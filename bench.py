@@ -4,10 +4,11 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
 
 Own arm.  Workload = BASELINE.json configs[1]: synthetic chr22 PacBio HiFi 30x (~15 kb reads) with
-MM/ML 5mC CG tags, `freq -c m[CG] -m 0.8 -b`.  One step = one pass of the hot path (k_decode:
+MM/ML 5mC CG tags, `freq -c m[CG] -m 0.8 -b`.  One step = one pass of the hot path (decode stage:
 MM/ML decode, CIGAR mapping, context check, threshold, dense aggregation) over the whole batch.
   value   reads/s with inputs already resident in HBM (W warm-up + exactly K timed steps between
-          barrier+synchronize pairs; max over ranks); inputs (~1 GB) exceed the 126 MB L2.
+          barrier+synchronize pairs; max over ranks); inputs (~1 GB) exceed the 126 MB L2.  One step launches
+          the decode stage: k_flat_setup, k_decode_warp<PRE> and the two fallback kernels (4 launches).
   e2e     reads/s through the C ABI with HOST (pinned) buffers: per step reset counts, H2D of every
           batch chunk + kernels on pipelined streams, finalize (compaction) and D2H of the rows.
   roofline / cpu_baseline / clocks / gpu_launches: see the JSON keys.
@@ -364,7 +365,9 @@ def main():
                        "e2e_chunks": chunks, "e2e_steps": e2e_steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "kernel": "k_decode"},
+                         "kernel": "decode stage = k_flat_setup + k_decode_warp<3,PRE> (dominant, ~80% of the stage) + the two "
+                                   "fallback kernels for deferred reads; CUDA events on the launch stream bracket the whole stage",
+                         "reads_deferred_to_fallback_kernels": int(tm1.flat_deferred_reads - tm0.flat_deferred_reads)},
             "e2e": {"value": reads_all * e2e_steps / e2e_max, "unit": "reads/s",
                     "h2d_bytes_per_step": int(tmB.h2d_bytes // e2e_steps), "d2h_bytes_per_step": int(tmB.d2h_bytes // e2e_steps),
                     "ms_per_step": 1e3 * e2e_max / e2e_steps},

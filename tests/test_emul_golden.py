@@ -27,3 +27,21 @@ def test_scratch_paths(emul_lib, monkeypatch, name):
     case = [c for c in GOLDEN_CASES if c[0] == name][0]
     out = run_case(emul_lib, *case[1:])
     assert sorted_lines(out) == sorted_lines(golden_bytes(name))
+
+
+# The decode stage has three implementations that must agree: the split path (k_flat_setup + k_decode_warp<PRE>,
+# the default), the self-contained warp-per-read kernel, and the general CTA-per-read kernel (what the
+# other two defer reads to).  MMC_WARP_ARENA shrinks the per-warp shared-memory arena so that CIGAR / index
+# sampling and deferral actually happen on the small fixtures.
+PATHS = [("split", None), ("warp", None), ("general", None), ("split", "4608"), ("warp", "4400")]
+
+
+@pytest.mark.parametrize("path,arena", PATHS, ids=[f"{p}-{a or 'default'}" for p, a in PATHS])
+@pytest.mark.parametrize("name", ["test7.tsv", "test5a.tsv", "test17a.tsv", "test2b.tsv"])
+def test_decode_paths_agree(emul_lib, monkeypatch, path, arena, name):
+    monkeypatch.setenv("MMC_DECODE_PATH", path)
+    if arena:
+        monkeypatch.setenv("MMC_WARP_ARENA", arena)
+    case = [c for c in GOLDEN_CASES if c[0] == name][0]
+    out = run_case(emul_lib, *case[1:])
+    assert sorted_lines(out) == sorted_lines(golden_bytes(name))

@@ -65,3 +65,19 @@ def test_cuda_vs_reference_binary_live(cuda_lib, bam, args):
         ref_out = run_ref(sub, args, fa, path)
         out = run_case(cuda_lib, sub, args, bam, "chr22")
         assert sorted_lines(out) == sorted_lines(ref_out)
+
+
+PATHS = [("split", None, "3"), ("split", None, "4"), ("split", None, "2"), ("warp", None, "3"), ("general", None, "3"),
+         ("split", "4608", "3"), ("warp", "4400", "4")]
+
+
+@pytest.mark.parametrize("path,arena,occ", PATHS, ids=[f"{p}-{a or 'default'}-occ{o}" for p, a, o in PATHS])
+def test_cuda_decode_paths_agree(cuda_lib, monkeypatch, path, arena, occ):
+    """Split (default), warp-per-read and general kernels, arena sizes that force sampling / deferral."""
+    monkeypatch.setenv("MMC_DECODE_PATH", path)
+    monkeypatch.setenv("MMC_WARP_OCC", occ)
+    if arena:
+        monkeypatch.setenv("MMC_WARP_ARENA", arena)
+    for name in ("test7.tsv", "test5a.tsv", "test5c.tsv", "test17a.tsv", "test16.tsv", "test2b.tsv", "test11.tsv"):
+        case = [c for c in GOLDEN_CASES if c[0] == name][0]
+        assert sorted_lines(run_case(cuda_lib, *case[1:])) == sorted_lines(golden_bytes(name)), name

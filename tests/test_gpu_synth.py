@@ -30,8 +30,21 @@ def test_synthetic_parity_cuda(cuda_lib, config, cov, sub):
 @pytest.mark.parametrize("small_smem", ["0", "1"])
 def test_synthetic_parity_cuda_scratch(cuda_lib, monkeypatch, small_smem):
     monkeypatch.setenv("MMC_TEST_SMALL_SMEM", small_smem)
+    monkeypatch.setenv("MMC_DECODE_PATH", "general")
     run_synth(cuda_lib, 3, 800000, 2.0, "freq")
     run_synth(cuda_lib, 4, 800000, 0.5, "freq")
+
+
+@pytest.mark.parametrize("path,arena", [("split", None), ("warp", None), ("split", "5120"), ("general", None)])
+@pytest.mark.parametrize("config,cov", [(2, 3.0), (3, 2.0), (6, 1.5), (4, 0.5)])
+def test_synthetic_parity_cuda_paths(cuda_lib, monkeypatch, path, arena, config, cov):
+    """Every decode path against the oracle on every config shape (50 kb reads of config 4 are mostly deferred
+    by the warp kernels; the small arena forces CIGAR / index sampling and more deferral)."""
+    monkeypatch.setenv("MMC_DECODE_PATH", path)
+    if arena:
+        monkeypatch.setenv("MMC_WARP_ARENA", arena)
+    n, st = run_synth(cuda_lib, config, 1000000, cov, "freq")
+    assert n > 0
 
 
 def test_counts_are_linear_in_passes(cuda_lib):
