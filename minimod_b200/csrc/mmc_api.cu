@@ -78,7 +78,7 @@ struct mmc_ctx {
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
     uint32_t setup_arena_bytes = kWReadBytes + 4608;   // k_flat_setup: WRead + 1152 words for dir | cq | cr
-    int w_minb = 3;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
+    int w_minb = 4;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
     uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
     int n_code_slots = 1, n_hap_slots = 1, wild_req = -1;
     ReqMod *d_req = nullptr;

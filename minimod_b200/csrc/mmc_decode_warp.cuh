@@ -92,7 +92,6 @@ struct WTile {                               // per warp, shared memory: one tex
     uint4    text[32 + 1];                   // chunk i at text[i] (+ one spill-over chunk)
     uint32_t em[32];                         // per chunk: terminator mask (',' or block end) of its 32 following bytes
     uint32_t rank[kWTokCap];                 // per token: byte offset in text -> base rank -> read position q
-    int32_t  refp[kWTokCap];                 // per call: reference position (aln[q]) or -1
 };
 
 struct WFixed {                              // fixed part of a warp's arena on the fused path
@@ -616,7 +615,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     uint32_t gshift = 8;
     while (((L >> gshift) + 2u) > 160u) ++gshift;
     const uint32_t n_dir = (L >> gshift) + 2u;
-    const uint32_t n_rd = (L >> 5) + 2u;
+    const uint32_t n_rd = (L >> 6) + 2u;
     const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
     const uint32_t n_idx = idx_mask ? 1u : 0u, n_bm = bm_mask ? 1u : 0u;             // one index / bitmap, reused block after block
     const uint32_t cap = flex_words;
@@ -940,11 +939,9 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 4 (per text tile): the explicit calls whose ranks are in T->rank[0..n).  Three passes
-// staged through shared memory so that each is a short loop with independent iterations:
-//   select  base rank -> read position q            (bases_pos[][], src/mod.c:1102-1113)
-//   map     q -> reference position                 (aln[], src/mod.c:1122)
-//   update  context test, ML threshold, count cell  (src/mod.c:1140-1199)
+// phase 4 (per text tile), general form: the explicit calls whose ranks are in T->rank[0..n), in two passes
+//   select        base rank -> read position q                                 (bases_pos[][], src/mod.c:1102-1113)
+//   map + update  q -> reference position, context test, ML threshold, count   (src/mod.c:1122-1199)
 // ---------------------------------------------------------------------------------------
 constexpr uint32_t kNoCall = 0xffffffffu;
 
@@ -981,23 +978,10 @@ __device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WT
         }
     } else if (cls == 0u) w_pass_select<true>(R, T, flex, bd, pat, n, need_bm, lane);
     else w_pass_select<false>(R, T, flex, bd, pat, n, need_bm, lane);
-    if (P.insertions) {                                           // ins[] fall-back and ins_offset: fused map + update
-        for (uint32_t c = lane; c < n; c += 32u) {
-            const uint32_t q = T->rank[c];
-            if (q != kNoCall) w_call(P, R, flex, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
-        }
-        return;
-    }
-    // ---- map
+    // ---- map + update
     for (uint32_t c = lane; c < n; c += 32u) {
         const uint32_t q = T->rank[c];
-        T->refp[c] = q != kNoCall ? w_cigar_lookup(S, flex, q).aln : -1;
-    }
-    // ---- update
-    for (uint32_t c = lane; c < n; c += 32u) {
-        const int32_t ref_pos = T->refp[c];
-        if (ref_pos < 0) continue;                                // src/mod.c:1127
-        w_call_at(P, R, s_lut, bd, jb, T->rank[c], ref_pos, 0u, false, cidx0 + c, ml_base, rd_code);
+        if (q != kNoCall) w_call(P, R, flex, s_lut, bd, jb, q, false, cidx0 + c, ml_base, rd_code);
     }
 }
 
