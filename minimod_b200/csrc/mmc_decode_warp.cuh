@@ -90,6 +90,7 @@ struct WRead {                               // per read: shared memory (fused p
 
 struct WTile {                               // per warp, shared memory: one text tile of a block
     uint4    text[32 + 1];                   // chunk i at text[i] (+ one spill-over chunk)
+    uint32_t em[32];                         // per chunk: terminator mask (',' or block end) of its 32 following bytes
     uint32_t rank[kWTokCap];                 // per token: byte offset in text -> base rank -> read position q
 };
 
@@ -808,44 +809,47 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
     if (lane >= (uint32_t)kWChunks) st = 0;
     uint32_t em = cm | (ncm << 16);                               // token terminators: ',' or the block end
     if (a1 >= p0 && a1 - p0 < 32u) em |= 1u << (a1 - p0);
+    T->em[lane] = em;
     const uint32_t n_tok = (uint32_t)__popc(st);
     const uint32_t incl = warp_incl_scan(n_tok, lane);
     const uint32_t tile_cnt = __shfl_sync(kFull, incl, 31);
-    const uint32_t slot = incl - n_tok;
-    __syncwarp();                                                 // text of the next chunk is read below
-    // every lane parses the (<= 8) skip counts that start in its chunk: SWAR decimal, running sum of skip+1
-    const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(T->text);
+    uint32_t slot = incl - n_tok;
     const uint32_t base_off = lane * 16u;
-    uint32_t acc = 0, k = 0;
-    while (st) {
-        const uint32_t bpos = (uint32_t)__ffs((int)st) - 1u;
+    while (st) {                                                  // byte offset of every token of this chunk
+        T->rank[slot++] = base_off + (uint32_t)__ffs((int)st) - 1u;
         st &= st - 1u;
-        const uint32_t rest = em >> (bpos + 1u);
-        uint32_t nd = rest ? (uint32_t)__ffs((int)rest) : 32u, val = 0, bad = 0;
-        if (nd > 9u) { bad = 1; nd = 0; }                         // src/mod.c:1080-1085
-        const uint32_t off = base_off + bpos;
-        if (nd <= 4u) {
-            const uint32_t w0 = tx32[off >> 2], w1 = tx32[(off >> 2) + 1u];
-            uint32_t dg = __funnelshift_r(w0, w1, (off & 3u) * 8u) - 0x30303030u;
-            const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
-            bad |= (((dg + 0x76767676u) | dg) & 0x80808080u & keep) != 0u;
-            dg = (dg & keep) << ((8u * (4u - nd)) & 31u);
-            if (nd == 0u) dg = 0;
-            const uint32_t pr = (dg * 10u + (dg >> 8)) & 0x00ff00ffu;                  // (10*b0+b1) | (10*b2+b3) << 16
-            val = (pr & 0xffffu) * 100u + (pr >> 16);
-        } else {
-            val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
-        }
-        if (bad) { w_raise(R, kErrMMSkip); val = 0; }
-        acc += val + 1u;
-        if (acc > kWMaxL) acc = kWMaxL;                           // >= 2^26 is past any read this path takes; 32 of them fit 32 bits
-        T->rank[slot + k] = acc;                                  // lane-local inclusive sum
-        ++k;
     }
-    const uint32_t lsum = warp_incl_scan(acc, lane);              // <= 2^31
-    const uint32_t total = __shfl_sync(kFull, lsum, 31);
-    const uint32_t lbase = sat_add(carry_in, lsum - acc);
-    for (uint32_t j = 0; j < k; ++j) T->rank[slot + j] = sat_add(lbase, T->rank[slot + j]) - 1u;   // base_rank (src/mod.c:1098)
+    __syncwarp();
+    const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(T->text);
+    uint32_t carry = carry_in, total = 0;
+    for (uint32_t c0 = 0; c0 < tile_cnt; c0 += 32u) {
+        const uint32_t c = c0 + lane;
+        uint32_t x = 0;
+        if (c < tile_cnt) {                                       // one token per lane: SWAR decimal parse
+            const uint32_t off = T->rank[c];
+            const uint32_t rest = T->em[off >> 4] >> ((off & 15u) + 1u);
+            uint32_t nd = rest ? (uint32_t)__ffs((int)rest) : 32u, val = 0, bad = 0;
+            if (nd > 9u) { bad = 1; nd = 0; }                     // src/mod.c:1080-1085
+            if (nd <= 4u) {
+                const uint32_t w0 = tx32[off >> 2], w1 = tx32[(off >> 2) + 1u];
+                uint32_t dg = __funnelshift_r(w0, w1, (off & 3u) * 8u) - 0x30303030u;
+                const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
+                bad |= (((dg + 0x76767676u) | dg) & 0x80808080u & keep) != 0u;
+                dg = (dg & keep) << ((8u * (4u - nd)) & 31u);
+                if (nd == 0u) dg = 0;
+                const uint32_t pr = (dg * 10u + (dg >> 8)) & 0x00ff00ffu;              // (10*b0+b1) | (10*b2+b3) << 16
+                val = (pr & 0xffffu) * 100u + (pr >> 16);
+            } else {
+                val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
+            }
+            if (bad) { w_raise(R, kErrMMSkip); val = 0; }
+            x = val + 1u < kWMaxL ? val + 1u : kWMaxL;             // >= 2^26 is past any read this path takes; 32 of them fit 32 bits
+        }
+        const uint32_t si = warp_incl_scan(x, lane);
+        if (c < tile_cnt) T->rank[c] = sat_add(carry, si) - 1u;   // base_rank (src/mod.c:1098)
+        const uint32_t rt = __shfl_sync(kFull, si, 31);
+        carry = sat_add(carry, rt); total = sat_add(total, rt);
+    }
     *sum_out = total;
     __syncwarp();
     return tile_cnt;
