@@ -76,10 +76,14 @@ struct mmc_ctx {
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
-    int warp_path = 1, w_ctas_per_sm = 1;      // then k_decode_warp, then k_decode for what that defers
-    uint32_t setup_arena_bytes = kWReadBytes + 4608;   // k_flat_setup: WRead + 1152 words for dir | cq | cr
-    int w_minb = 4;                            // k_decode_warp<MINB>: resident CTAs per SM it is register-bounded for
-    uint32_t w_arena_bytes = 0;                // shared memory per warp of k_decode_warp (0: derived from w_minb)
+    int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
+    // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
+    // [0] unused; chosen per batch from the reads' sizes unless MMC_WARP_OCC pins one.
+    uint32_t wv_arena[5] = {0, 28672u, 14208u, 9344u, 6912u};   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
+    uint32_t wv_setup_arena[5] = {0, 0, 0, 0, 0};               // k_flat_setup: WRead + room for dir | cq | cr
+    int wv_ctas[5] = {0, 1, 1, 1, 1};
+    int w_pinned = 0;                          // MMC_WARP_OCC / MMC_WARP_ARENA given: no per-batch choice
+    int w_minb = 3;                            // default variant (3 CTAs/SM, 80 registers: best on 15 kb reads)
     int n_code_slots = 1, n_hap_slots = 1, wild_req = -1;
     ReqMod *d_req = nullptr;
     unsigned long long *d_code_keys = nullptr;
@@ -103,6 +107,7 @@ struct mmc_ctx {
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
     // results
     std::vector<mmc_freq_rec_t> freq_out;
+    std::vector<uint32_t> need_tmp;
     std::vector<std::string> code_names;
     mmc_timers_t tm{};
     int32_t cig_smem_cap = kCigSmem, bitmap_smem_words = kBitmapWords, idx_smem_cap = kIdxSmem;
@@ -257,14 +262,26 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     if (n == 0) { s.in_flight = true; s.timed = false; return MMC_OK; }
 
     uint32_t max_cig = 0, max_l = 0;
-    uint64_t pool_need = 0;                    // flat path: words of scratch if every read had two base classes and two '.' blocks
+    uint64_t pool_need = 0;                    // split path: words of scratch for every read's dir | cq | cr
+    std::vector<uint32_t> &need = ctx->need_tmp;   // per read: arena words for un-sampled CIGAR arrays + rank index
+    need.resize(n);
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
         max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
         const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
-        pool_need += 164 + 2ull * nc + 8;      // dir | cq | cr
-        (void)n_u4;
+        pool_need += 164 + 2ull * nc + 8;
+        need[i] = (uint32_t)std::min<uint64_t>(0xffffffffu, (L >> 8) + 2 + 2ull * nc + n_u4 + 2 + (L >> 6) + 2 + 12);
     }
+    // variant for this batch: the most CTAs per SM whose arena holds ~95% of the reads without sampling
+    int mb = ctx->w_minb;
+    if (!ctx->w_pinned && n > 0) {
+        const size_t k = (size_t)((uint64_t)(n - 1) * 95 / 100);
+        std::nth_element(need.begin(), need.begin() + k, need.end());
+        const uint32_t p95 = need[k];
+        mb = 3;
+        while (mb > 1 && (ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed)) / 4u < p95) --mb;
+    }
+    const uint32_t w_arena_bytes = ctx->wv_arena[mb], setup_arena_bytes = ctx->wv_setup_arena[mb];
     unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     if (grid == 0) grid = 1;
     uint32_t cig_words = max_cig > (uint32_t)ctx->cig_smem_cap ? (uint32_t)align_up(max_cig, 32) : 0;
@@ -326,24 +343,25 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     if (ctx->warp_path) {
         // fast path: one warp per read; reads that do not fit a warp's shared-memory arena go to the list
         WarpParams W;
-        W.arena_bytes = ctx->w_arena_bytes; W.defer_list = s.d_defer; W.defer_n = st32 + 5;
+        W.arena_bytes = w_arena_bytes; W.defer_list = s.d_defer; W.defer_n = st32 + 5;
         const uint64_t warps = n;                             // one warp per read, persistent above the resident limit
-        unsigned wgrid = (unsigned)std::min<uint64_t>((warps + kWThreads / 32 - 1) / (kWThreads / 32), (uint64_t)ctx->sm_count * ctx->w_ctas_per_sm);
+        unsigned wgrid = (unsigned)std::min<uint64_t>((warps + kWThreads / 32 - 1) / (kWThreads / 32), (uint64_t)ctx->sm_count * ctx->wv_ctas[mb]);
         if (wgrid == 0) wgrid = 1;
-        const size_t wsmem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
+        const size_t wsmem = (size_t)kWLutSlots * 256 + (size_t)w_arena_bytes * (kWThreads / 32);
         PreParams Q; Q.reads = nullptr; Q.n = 0;
         if (ctx->split_path) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
-            F.arena_bytes = ctx->setup_arena_bytes;
-            F.consumer_flex_words = (ctx->w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
+            F.arena_bytes = setup_arena_bytes;
+            F.consumer_flex_words = (w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
             F.read_count = n;
             const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
-            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWLutSlots * 256 + (size_t)ctx->setup_arena_bytes * (kFThreads / 32), s.stream, P, F);
+            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWLutSlots * 256 + (size_t)setup_arena_bytes * (kFThreads / 32), s.stream, P, F);
             CU(ctx, cudaGetLastError());
             ctx->tm.kernel_launches += 1;
             Q.reads = s.d_reads; Q.n = n;
-            if (ctx->w_minb == 2) MMC_LAUNCH_SMEM((k_decode_warp<2, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
-            else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM((k_decode_warp<3, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+            if (mb == 1) MMC_LAUNCH_SMEM((k_decode_warp<1, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+            else if (mb == 2) MMC_LAUNCH_SMEM((k_decode_warp<2, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+            else if (mb == 3) MMC_LAUNCH_SMEM((k_decode_warp<3, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
             else MMC_LAUNCH_SMEM((k_decode_warp<4, true>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
             CU(ctx, cudaGetLastError());
             ctx->tm.kernel_launches += 1;
@@ -351,8 +369,9 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
             P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7; P.work_counter = st32 + 12;
             Q.reads = nullptr; Q.n = 0;
         }
-        if (ctx->w_minb == 2) MMC_LAUNCH_SMEM((k_decode_warp<2, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
-        else if (ctx->w_minb == 3) MMC_LAUNCH_SMEM((k_decode_warp<3, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+        if (mb == 1) MMC_LAUNCH_SMEM((k_decode_warp<1, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+        else if (mb == 2) MMC_LAUNCH_SMEM((k_decode_warp<2, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
+        else if (mb == 3) MMC_LAUNCH_SMEM((k_decode_warp<3, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
         else MMC_LAUNCH_SMEM((k_decode_warp<4, false>), wgrid, (unsigned)kWThreads, wsmem, s.stream, P, W, Q);
         CU(ctx, cudaGetLastError());
         ctx->tm.kernel_launches += 1;
@@ -438,11 +457,14 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         else if (!strcmp(e, "warp")) ctx->split_path = 0;
         else if (!strcmp(e, "split")) ctx->split_path = 1;
     }
-    if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) ctx->w_minb = v; }   // tuning
-    ctx->w_arena_bytes = ctx->w_minb == 2 ? 14208u : ctx->w_minb == 3 ? 9344u : 6912u;   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
+    if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
         long v = atol(e);
-        if (v >= (long)sizeof(WFixed) + 256 && v <= 27 * 1024) ctx->w_arena_bytes = (uint32_t)(v & ~15l);
+        if (v >= (long)sizeof(WFixed) + 256 && v <= 28 * 1024) { ctx->wv_arena[ctx->w_minb] = (uint32_t)(v & ~15l); ctx->w_pinned = 1; }
+    }
+    for (int mb = 1; mb <= 4; ++mb) {                        // k_flat_setup holds WRead + the un-sampled CIGAR arrays of most reads
+        const uint32_t flex = ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed);
+        ctx->wv_setup_arena[mb] = kWReadBytes + std::min<uint32_t>(std::max<uint32_t>(4608u, (flex / 2u) & ~15u), 24576u);
     }
 
 #define CUC(call)                                                                                            \
@@ -463,19 +485,20 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_decode, ctx->threads, 0));
     ctx->ctas_per_sm = occ < 1 ? 1 : occ;
     {
-        const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->w_arena_bytes * (kWThreads / 32);
-        int wocc = 1;
+        size_t setup_max = 0;
+        for (int mb = 1; mb <= 4; ++mb) setup_max = std::max(setup_max, (size_t)kWLutSlots * 256 + (size_t)ctx->wv_setup_arena[mb] * (kFThreads / 32));
+        CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)setup_max));
 #define MMC_WARP_ATTR(MB)                                                                                                        \
         do {                                                                                                                     \
+            const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->wv_arena[MB] * (kWThreads / 32);                         \
+            int wocc = 1;                                                                                                        \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize,                                  \
-                                     (int)((size_t)kWLutSlots * 256 + (size_t)ctx->setup_arena_bytes * (kFThreads / 32))));      \
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, (k_decode_warp<MB, true>), kWThreads, smem));               \
+            ctx->wv_ctas[MB] = wocc < 1 ? 1 : wocc;                                                                              \
         } while (0)
-        if (ctx->w_minb == 2) MMC_WARP_ATTR(2); else if (ctx->w_minb == 3) MMC_WARP_ATTR(3); else MMC_WARP_ATTR(4);
+        MMC_WARP_ATTR(1); MMC_WARP_ATTR(2); MMC_WARP_ATTR(3); MMC_WARP_ATTR(4);
 #undef MMC_WARP_ATTR
-        ctx->w_ctas_per_sm = wocc < 1 ? 1 : wocc;
     }
 
     // ---- -c entries -> device tables
