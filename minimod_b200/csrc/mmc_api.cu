@@ -270,9 +270,9 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
         const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
         pool_need += 164 + 2ull * nc + 8;
-        need[i] = (uint32_t)std::min<uint64_t>(0xffffffffu, (L >> 8) + 2 + 2ull * nc + n_u4 + 2 + (L >> 6) + 2 + 12);
+        need[i] = (uint32_t)std::min<uint64_t>(0xffffffffu, (L >> 8) + 2 + nc / 2 + n_u4 + 2 + (L >> 6) + 2 + 12);   // CIGAR sampled 1:4 at worst
     }
-    // variant for this batch: the most CTAs per SM whose arena holds ~95% of the reads without sampling
+    // variant for this batch: the most CTAs per SM whose arena holds ~95% of the reads with an un-sampled index
     int mb = ctx->w_minb;
     if (!ctx->w_pinned && n > 0) {
         const size_t k = (size_t)((uint64_t)(n - 1) * 95 / 100);

@@ -856,17 +856,19 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 4, common case in one tight loop: one requested code per block (K == 1), canonical base
-// C/G/T, `freq` without --insertions/--haplotypes, context "*" or <= 8 ACGT bases, un-sampled
-// CIGAR and index.  Same arithmetic as the staged passes below, no generality.
+// phase 4, common case in one tight loop: `freq`, one requested code per block (K == 1), canonical base
+// A/C/G/T, context "*" or <= 8 ACGT bases, un-sampled CIGAR and index, haplotype (if any) with a
+// dense stratum.  Same arithmetic as the general passes below.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ bool w_fast_ok(const DecodeParams &P, const WState &S, const WBlock *bd) {
     const WCode cd = bd->code[0];
-    return bd->K == 1 && cd.ri >= 0 && cd.ri < kWLutSlots && P.subtool == 1 && !P.insertions && !P.haplotypes &&
-           cd.ctx_mode != kCtxSlow && !bd->is_n && bd->cls != 0u && bd->cls != 4u && S.cshift == 0u && S.ishift == 0u &&
+    return bd->K == 1 && cd.ri >= 0 && cd.ri < kWLutSlots && P.subtool == 1 &&
+           (!P.haplotypes || (int32_t)S.hp + 1 < P.n_hap_slots) &&
+           cd.ctx_mode != kCtxSlow && !bd->is_n && bd->cls != 4u && S.ishift == 0u &&
            (uint32_t)cd.outc < (uint32_t)P.n_code_slots;
 }
 
+template <bool C0>
 __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *R, WTile *T, uint32_t *flex, const uint8_t *s_lut, const WBlock *bd,
                                                   uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
@@ -884,6 +886,7 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
     const uint8_t *lut = s_lut + cd.ri * 256;
     const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
     const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
+    const uint32_t hslot = P.haplotypes ? S.hp + 1u : 0u, insertions = (uint32_t)P.insertions, cshift = S.cshift;
     const uint32_t ml0 = ml_base + cidx0;
     for (uint32_t c = lane; c < n; c += 32u) {
         const uint32_t rank = T->rank[c];
@@ -896,7 +899,7 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
         while (nxt <= k) { ++e; nxt = idx[e + 1u]; }
         uint32_t rem = k - idx[e];
         const uint4 v = ld16(seq + (size_t)e * 16u);
-        const uint32_t f0 = nib_eq_flags(v.x, pat), f1 = nib_eq_flags(v.y, pat), f2 = nib_eq_flags(v.z, pat), f3 = nib_eq_flags(v.w, pat);
+        const uint32_t f0 = class_flags<C0>(v.x, pat), f1 = class_flags<C0>(v.y, pat), f2 = class_flags<C0>(v.z, pat), f3 = class_flags<C0>(v.w, pat);
         const uint32_t s0 = (uint32_t)__popc(f0), s1 = s0 + (uint32_t)__popc(f1), s2 = s1 + (uint32_t)__popc(f2);
         uint32_t f = f0, wsel = 0, sub = 0;
         if (rem >= s0) { f = f1; wsel = 8; sub = s0; }
@@ -910,14 +913,26 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
         const uint32_t q = e * 32u + wsel + ((rem != 0u || !(f & 0x80u)) ? 1u : 0u);
         if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
         // ---- map: aln[q]
+        uint32_t ref_pos, ins16 = 0;
+        if (cshift != 0u) {                                                         // sampled CIGAR (long reads): generic lookup
+            const AlnHit h = w_cigar_lookup(S, flex, q);
+            if (h.aln >= 0) ref_pos = (uint32_t)h.aln;
+            else if (insertions && h.ins >= 0) { ref_pos = (uint32_t)h.ins; ins16 = h.insoff & 0xffffu; }
+            else continue;
+        } else {
         if (q >= total_q) continue;
         const uint32_t b = q >> g;
         uint32_t lo = dir[b], hi = (((b + 1u) << g) < total_q) ? dir[b + 1u] : last_samp;
         const uint32_t qlim = (q + 1u) << 4;
         while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (cq[mid] < qlim) lo = mid; else hi = mid - 1u; }
         const uint32_t ce = cq[lo], op = ce & 15u;
-        if (op != 0u && op != 7u && op != 8u) continue;                             // src/mod.c:1127
-        const uint32_t ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
+        if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
+        else if (insertions && op == 1u) {                                          // ins[] / ins_offset (src/mod.c:1122-1127)
+            const int32_t left = pos + (int32_t)cr[lo] - 1;
+            if (left < 0) continue;                                                 // Q11
+            ref_pos = (uint32_t)left; ins16 = (q - (ce >> 4) + 1u) & 0xffffu;       // make_key's uint16_t (src/mod.c:428)
+        } else continue;                                                            // src/mod.c:1127
+        }
         // ---- update
         if (m) {
             if (ref_pos + 1u < m || ref_pos + m > ref_len) {                        // contig edge: generic test
@@ -928,13 +943,27 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
                 const uint32_t E = __funnelshift_r(ldg32(excm + ei), ldg32(excm + ei + 1u), w0 & 31u);
                 uint32_t hit = 0;
                 for (uint32_t j = 0; j < m; ++j) hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
-                if (!hit || ((W >> (2u * (m - 1u))) & 3u) != cls) continue;         // src/mod.c:1162-1172
+                if (!hit) continue;                                                 // src/mod.c:1162-1172
+                uint32_t rc = cls;                                                  // the read base, as a 2-bit code
+                if (C0) {                                                           // class 0 = 'A' and every other nt16 letter
+                    const uint32_t nib = (ldg8(seq + (q >> 1)) >> ((~q & 1u) << 2)) & 0xfu;
+                    rc = nib == 1u ? 0u : 5u;
+                }
+                if (((W >> (2u * (m - 1u))) & 3u) != rc) continue;
             }
         }
         if (prob > 0xffu) { w_raise(R, kErrMLIndex); continue; }                    // src/mod.c:1174
         const uint32_t fl = lut[prob];                                              // src/mod.c:1181-1191
         if (!(fl & 1u)) continue;
-        red_add_u64(cells + ((unsigned long long)ref_pos * per_pos + within), 1ull | ((unsigned long long)((fl >> 1) & 1u) << 32));
+        const unsigned long long inc = 1ull | ((unsigned long long)((fl >> 1) & 1u) << 32);
+        if (ins16 == 0u) {
+            unsigned long long *cell = cells + ((unsigned long long)ref_pos * per_pos + within);
+            red_add_u64(cell, inc);                                                 // the '*' stratum (or the only one)
+            if (hslot) red_add_u64(cell + hslot, inc);                              // src/mod.c:906-928
+        } else {
+            if (hslot) w_add_sparse(P, (uint32_t)S.tid, rev, (int32_t)ref_pos, cd.outc, ins16, (int32_t)S.hp, (fl >> 1) & 1u);
+            w_add_sparse(P, (uint32_t)S.tid, rev, (int32_t)ref_pos, cd.outc, ins16, -1, (fl >> 1) & 1u);
+        }
     }
 }
 
@@ -963,7 +992,11 @@ __device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WT
                                              uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
     const WBlock *bd = &R->blk[slot];                              // jb: the block's ordinal in the read (view row order)
-    if (w_fast_ok(P, S, bd)) { w_tile_calls_fast(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); return; }
+    if (w_fast_ok(P, S, bd)) {
+        if (bd->cls == 0u) w_tile_calls_fast<true>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane);
+        else w_tile_calls_fast<false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane);
+        return;
+    }
     const uint32_t cls = bd->cls, need_bm = bd->dot;
     const uint32_t pat = class_pat(cls), rd_code = cls >= 1u && cls <= 3u ? cls : 4u;
     // ---- select
