@@ -331,7 +331,16 @@ __device__ __noinline__ bool w_ctx_slow(const DecodeParams &P, const WState &S, 
 // a count outside the dense arrays (ins_offset > 0, exotic haplotype / code id): cold
 __device__ __noinline__ void w_add_sparse(const DecodeParams &P, uint32_t tid, uint32_t rev, int32_t ref_pos, uint32_t outc,
                                           uint32_t ins16, int32_t hap, uint32_t is_mod) {
+#ifdef MMC_EMUL
     unsigned long long slot = atomicAdd(P.sparse_n, 1ull);
+#else
+    // one atomic per warp: the lanes that are here together take consecutive slots
+    const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)act) - 1u;
+    unsigned long long slot = 0;
+    if (lane_id == leader) slot = atomicAdd(P.sparse_n, (unsigned long long)__popc(act));
+    slot = (((unsigned long long)__shfl_sync(act, (uint32_t)(slot >> 32), (int)leader)) << 32) | __shfl_sync(act, (uint32_t)slot, (int)leader);
+    slot += (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
+#endif
     if (slot < P.sparse_cap) {
         SparseRec s;
         s.a = ((unsigned long long)tid << 41) | ((unsigned long long)(uint32_t)ref_pos << 9) | ((unsigned long long)rev << 8) | outc;
@@ -868,7 +877,9 @@ __device__ __forceinline__ bool w_fast_ok(const DecodeParams &P, const WState &S
            (uint32_t)cd.outc < (uint32_t)P.n_code_slots;
 }
 
-template <bool C0>
+//   C0  class A (needs the nibble of the read base for the reference comparison)
+//   EX  any of: --insertions, --haplotypes, sampled CIGAR (kept out of the lean instantiation)
+template <bool C0, bool EX>
 __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *R, WTile *T, uint32_t *flex, const uint8_t *s_lut, const WBlock *bd,
                                                   uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
@@ -886,7 +897,7 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
     const uint8_t *lut = s_lut + cd.ri * 256;
     const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
     const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
-    const uint32_t hslot = P.haplotypes ? S.hp + 1u : 0u, insertions = (uint32_t)P.insertions, cshift = S.cshift;
+    const uint32_t hslot = EX && P.haplotypes ? S.hp + 1u : 0u, insertions = EX ? (uint32_t)P.insertions : 0u, cshift = EX ? S.cshift : 0u;
     const uint32_t ml0 = ml_base + cidx0;
     for (uint32_t c = lane; c < n; c += 32u) {
         const uint32_t rank = T->rank[c];
@@ -914,7 +925,7 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
         if (need_bm) atomicOr(&bm[rank >> 5], 1u << (rank & 31u));
         // ---- map: aln[q]
         uint32_t ref_pos, ins16 = 0;
-        if (cshift != 0u) {                                                         // sampled CIGAR (long reads): generic lookup
+        if (EX && cshift != 0u) {                                                   // sampled CIGAR (long reads): generic lookup
             const AlnHit h = w_cigar_lookup(S, flex, q);
             if (h.aln >= 0) ref_pos = (uint32_t)h.aln;
             else if (insertions && h.ins >= 0) { ref_pos = (uint32_t)h.ins; ins16 = h.insoff & 0xffffu; }
@@ -927,7 +938,7 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
         while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (cq[mid] < qlim) lo = mid; else hi = mid - 1u; }
         const uint32_t ce = cq[lo], op = ce & 15u;
         if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
-        else if (insertions && op == 1u) {                                          // ins[] / ins_offset (src/mod.c:1122-1127)
+        else if (EX && insertions && op == 1u) {                                    // ins[] / ins_offset (src/mod.c:1122-1127)
             const int32_t left = pos + (int32_t)cr[lo] - 1;
             if (left < 0) continue;                                                 // Q11
             ref_pos = (uint32_t)left; ins16 = (q - (ce >> 4) + 1u) & 0xffffu;       // make_key's uint16_t (src/mod.c:428)
@@ -956,10 +967,10 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
         const uint32_t fl = lut[prob];                                              // src/mod.c:1181-1191
         if (!(fl & 1u)) continue;
         const unsigned long long inc = 1ull | ((unsigned long long)((fl >> 1) & 1u) << 32);
-        if (ins16 == 0u) {
+        if (!EX || ins16 == 0u) {
             unsigned long long *cell = cells + ((unsigned long long)ref_pos * per_pos + within);
             red_add_u64(cell, inc);                                                 // the '*' stratum (or the only one)
-            if (hslot) red_add_u64(cell + hslot, inc);                              // src/mod.c:906-928
+            if (EX && hslot) red_add_u64(cell + hslot, inc);                        // src/mod.c:906-928
         } else {
             if (hslot) w_add_sparse(P, (uint32_t)S.tid, rev, (int32_t)ref_pos, cd.outc, ins16, (int32_t)S.hp, (fl >> 1) & 1u);
             w_add_sparse(P, (uint32_t)S.tid, rev, (int32_t)ref_pos, cd.outc, ins16, -1, (fl >> 1) & 1u);
@@ -993,8 +1004,9 @@ __device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WT
     const WState &S = R->st;
     const WBlock *bd = &R->blk[slot];                              // jb: the block's ordinal in the read (view row order)
     if (w_fast_ok(P, S, bd)) {
-        if (bd->cls == 0u) w_tile_calls_fast<true>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane);
-        else w_tile_calls_fast<false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane);
+        const bool ex = P.insertions || P.haplotypes || S.cshift != 0u;
+        if (bd->cls == 0u) { if (ex) w_tile_calls_fast<true, true>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); else w_tile_calls_fast<true, false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); }
+        else { if (ex) w_tile_calls_fast<false, true>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); else w_tile_calls_fast<false, false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); }
         return;
     }
     const uint32_t cls = bd->cls, need_bm = bd->dot;
