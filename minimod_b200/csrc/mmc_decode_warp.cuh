@@ -999,14 +999,25 @@ __device__ __forceinline__ void w_pass_select(WRead *R, WTile *T, uint32_t *flex
     }
 }
 
-__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, WRead *R, WTile *T, uint32_t *flex, const uint8_t *s_lut, uint32_t slot, uint32_t jb,
+__device__ __noinline__ void w_tile_calls_fast_other(const DecodeParams &P, uint32_t aoff, uint32_t slot, uint32_t n, uint32_t cidx0,
+                                                     uint32_t ml_base, uint32_t lane) {
+    const WArena A = w_arena(aoff);
+    const WBlock *bd = &A.R->blk[slot];
+    const bool ex = P.insertions || P.haplotypes || A.R->st.cshift != 0u;
+    if (bd->cls == 0u) {
+        if (ex) w_tile_calls_fast<true, true>(P, A.R, A.T, A.flex, A.s_lut, bd, n, cidx0, ml_base, lane);
+        else w_tile_calls_fast<true, false>(P, A.R, A.T, A.flex, A.s_lut, bd, n, cidx0, ml_base, lane);
+    } else w_tile_calls_fast<false, true>(P, A.R, A.T, A.flex, A.s_lut, bd, n, cidx0, ml_base, lane);
+}
+
+__device__ __forceinline__ void w_tile_calls(const DecodeParams &P, uint32_t aoff, WRead *R, WTile *T, uint32_t *flex, const uint8_t *s_lut, uint32_t slot, uint32_t jb,
                                              uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
     const WBlock *bd = &R->blk[slot];                              // jb: the block's ordinal in the read (view row order)
     if (w_fast_ok(P, S, bd)) {
         const bool ex = P.insertions || P.haplotypes || S.cshift != 0u;
-        if (bd->cls == 0u) { if (ex) w_tile_calls_fast<true, true>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); else w_tile_calls_fast<true, false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); }
-        else { if (ex) w_tile_calls_fast<false, true>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); else w_tile_calls_fast<false, false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane); }
+        if (ex || bd->cls == 0u) w_tile_calls_fast_other(P, aoff, slot, n, cidx0, ml_base, lane);   // own function: own registers
+        else w_tile_calls_fast<false, false>(P, R, T, flex, s_lut, bd, n, cidx0, ml_base, lane);
         return;
     }
     const uint32_t cls = bd->cls, need_bm = bd->dot;
@@ -1085,7 +1096,7 @@ __device__ __noinline__ uint32_t w_fused_tile(const DecodeParams &P, uint32_t ao
     const WBlock *bd = &R->blk[jb];
     uint32_t sum = 0;
     const uint32_t n = w_tile_ranks(R, A.T, tb, bd->hdr_end, bd->end, S.carry_sum, &sum, lane);
-    if (bd->any_req && n) w_tile_calls(P, R, A.T, A.flex, A.s_lut, jb, jb, n, carry_cnt, ml_base, lane);
+    if (bd->any_req && n) w_tile_calls(P, aoff, R, A.T, A.flex, A.s_lut, jb, jb, n, carry_cnt, ml_base, lane);
     __syncwarp();
     if (lane == 0) S.carry_sum = sat_add(S.carry_sum, sum);
     __syncwarp();
