@@ -610,6 +610,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
         herr = w_parse_header<TILE>(P, aoff, lane);
         if (herr == kErrNone) { my_idx = w_needs_index(&R->blk[lane]); my_bm = w_needs_bitmap(&R->blk[lane]); my_cls = R->blk[lane].cls; }
     }
+    __syncwarp();                                                                    // block table complete before lane 0 extends it
     const uint32_t herr_mask = __ballot_sync(kFull, herr != kErrNone);
     if (herr_mask) herr = __shfl_sync(kFull, herr, __ffs((int)herr_mask) - 1);
     const uint32_t idx_mask = __ballot_sync(kFull, my_idx != 0u), bm_mask = __ballot_sync(kFull, my_bm != 0u);
