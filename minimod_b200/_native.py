@@ -142,6 +142,7 @@ def _declare_host(lib):
         "mmh_fasta_seq": (vp, [vp, C.c_int]),
         "mmh_fasta_len": (C.c_uint64, [vp, C.c_int]),
         "mmh_parse_mods": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, P(MmcMod), C.c_int, C.c_char_p, C.c_int]),
+        "mmh_fastfmt_selftest": (C.c_longlong, [C.c_uint, C.c_ulonglong, C.c_char_p, C.c_int]),
         "mmh_write_freq": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_char_p), P(MmcFreqRec),
                                       C.c_uint64, C.c_int, P(C.c_char_p)]),
         "mmh_synth_new": (vp, [C.c_int, C.c_uint64, C.c_int, P(C.c_char_p), P(C.c_uint32), C.c_double]),

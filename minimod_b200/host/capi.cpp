@@ -9,6 +9,7 @@
 #include "bam.h"
 #include "fasta.h"
 #include "format.h"
+#include "fastfmt.h"
 #include "modopts.h"
 #include "pack.h"
 
@@ -97,6 +98,31 @@ int mmh_parse_mods(const char *codes, const char *threshes, int subtool, mmc_mod
 }
 
 // Format freq rows exactly as print_freq_header()+print_freq_output() would; append=0 truncates.
+// fastfmt.h against the C library: returns the number of mismatches of fmt_f6 vs snprintf("%f") over
+// (a) every n_mod/n_called and n_mod*100/n_called with 1 <= n_called <= max_den, 0 <= n_mod <= n_called,
+// (b) n_random pseudo-random pairs of 32-bit counts (n_mod <= n_called) and raw doubles in [0, 2^40).
+long long mmh_fastfmt_selftest(unsigned max_den, unsigned long long n_random, char *first_bad, int first_bad_len) {
+    long long bad = 0;
+    char a[64], b[64];
+    auto check = [&](double x) {
+        char *e = fmt_f6(a, x); *e = 0;
+        snprintf(b, sizeof b, "%f", x);
+        if (strcmp(a, b) != 0) { if (!bad && first_bad) snprintf(first_bad, first_bad_len, "%.17g: fmt_f6=%s printf=%s", x, a, b); ++bad; }
+    };
+    for (unsigned d = 1; d <= max_den; ++d)
+        for (unsigned n = 0; n <= d; ++n) { check((double)n / d); check((double)n * 100 / d); }
+    uint64_t s = 0x9e3779b97f4a7c15ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    for (unsigned long long i = 0; i < n_random; ++i) {
+        uint32_t d = (uint32_t)(rnd() >> (rnd() % 32 + 32)) | 1u, n = (uint32_t)(rnd() % ((uint64_t)d + 1));
+        check((double)n / d); check((double)n * 100 / d);
+        double x = (double)(rnd() >> 24) / (double)(1ull << (rnd() % 40));          // dyadic values: exact ties happen here
+        check(x);
+        check((double)((rnd() % 2000000) * 2 + 1) / 2097152.0);                      // k/2^21: many exact .5 ties at 6 decimals
+    }
+    return bad;
+}
+
 int mmh_write_freq(const char *path, int bedmethyl, int insertions, int haplotypes, int n_contigs, const char *const *contig_names,
                    const mmc_freq_rec_t *recs, uint64_t n, int n_codes, const char *const *code_names) {
     FILE *fp = fopen(path, "w");

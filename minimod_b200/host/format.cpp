@@ -1,4 +1,5 @@
 #include "format.h"
+#include "fastfmt.h"
 #include <algorithm>
 #include <string.h>
 
@@ -29,37 +30,68 @@ void print_freq_records(FILE *fp, const OutOpts &o, const std::vector<std::strin
     std::stable_sort(groups.begin(), groups.end(), [&](const Group &x, const Group &y) {
         return strcmp(names[x.tid].c_str(), names[y.tid].c_str()) < 0;
     });
+    // rows are formatted into a buffer with integer arithmetic only (fastfmt.h: fmt_f6 == printf("%f") exactly)
+    std::vector<char> buf(1u << 20);
+    char *p = buf.data(), *const flush_at = buf.data() + buf.size() - 512;
     for (const Group &g : groups) {
         const char *contig = names[g.tid].c_str();
+        const size_t contig_len = names[g.tid].size();
+        if (contig_len > 200) {                                      // absurd name: keep the simple path
+            if (p != buf.data()) { fwrite(buf.data(), 1, (size_t)(p - buf.data()), fp); p = buf.data(); }
+        }
         for (uint64_t i = g.b; i < g.e; ++i) {
             const mmc_freq_rec_t &r = recs[i];
-            const char *code = codes[r.code].c_str();
+            const std::string &code = codes[r.code];
             const char strand = r.strand ? '-' : '+';
-            if (o.bedmethyl) {                                       // src/mod.c:672-688
-                double f = (double)r.n_mod * 100 / r.n_called;
-                int end = r.pos + 1;
-                fprintf(fp, "%s\t%d\t%d\t%s\t%d\t%c\t%d\t%d\t255,0,0\t%d\t%f\n", contig, r.pos, end, code, (int)r.n_called,
-                        strand, r.pos, end, (int)r.n_called, f);
-            } else {                                                 // src/mod.c:691-718
-                double f = (double)r.n_mod / r.n_called;
-                fprintf(fp, "%s\t%d\t%d\t%c\t%d\t%d\t%f\t%s", contig, r.pos, r.pos, strand, (int)r.n_called, (int)r.n_mod, f, code);
-                if (o.insertions) fprintf(fp, "\t%d", (int)r.ins_offset);
-                if (o.haplotypes) { if (r.hap == -1) fputs("\t*", fp); else fprintf(fp, "\t%d", (int)r.hap); }
-                fputc('\n', fp);
+            if (contig_len > 200 || code.size() > 64) {              // fall back to stdio for pathological strings
+                if (o.bedmethyl) {
+                    double f = (double)r.n_mod * 100 / r.n_called;
+                    fprintf(fp, "%s\t%d\t%d\t%s\t%d\t%c\t%d\t%d\t255,0,0\t%d\t%f\n", contig, r.pos, r.pos + 1, code.c_str(), (int)r.n_called,
+                            strand, r.pos, r.pos + 1, (int)r.n_called, f);
+                } else {
+                    double f = (double)r.n_mod / r.n_called;
+                    fprintf(fp, "%s\t%d\t%d\t%c\t%d\t%d\t%f\t%s", contig, r.pos, r.pos, strand, (int)r.n_called, (int)r.n_mod, f, code.c_str());
+                    if (o.insertions) fprintf(fp, "\t%d", (int)r.ins_offset);
+                    if (o.haplotypes) { if (r.hap == -1) fputs("\t*", fp); else fprintf(fp, "\t%d", (int)r.hap); }
+                    fputc('\n', fp);
+                }
+                continue;
             }
+            memcpy(p, contig, contig_len); p += contig_len;
+            if (o.bedmethyl) {                                       // src/mod.c:672-688
+                const double f = (double)r.n_mod * 100 / r.n_called;
+                const int32_t end = r.pos + 1;
+                *p++ = '\t'; p = fmt_i32(p, r.pos); *p++ = '\t'; p = fmt_i32(p, end); *p++ = '\t';
+                memcpy(p, code.data(), code.size()); p += code.size();
+                *p++ = '\t'; p = fmt_i32(p, (int32_t)r.n_called); *p++ = '\t'; *p++ = strand;
+                *p++ = '\t'; p = fmt_i32(p, r.pos); *p++ = '\t'; p = fmt_i32(p, end);
+                p = fmt_str(p, "\t255,0,0\t"); p = fmt_i32(p, (int32_t)r.n_called); *p++ = '\t'; p = fmt_f6(p, f);
+            } else {                                                 // src/mod.c:691-718
+                const double f = (double)r.n_mod / r.n_called;
+                *p++ = '\t'; p = fmt_i32(p, r.pos); *p++ = '\t'; p = fmt_i32(p, r.pos); *p++ = '\t'; *p++ = strand;
+                *p++ = '\t'; p = fmt_i32(p, (int32_t)r.n_called); *p++ = '\t'; p = fmt_i32(p, (int32_t)r.n_mod);
+                *p++ = '\t'; p = fmt_f6(p, f); *p++ = '\t';
+                memcpy(p, code.data(), code.size()); p += code.size();
+                if (o.insertions) { *p++ = '\t'; p = fmt_i32(p, (int32_t)r.ins_offset); }
+                if (o.haplotypes) { *p++ = '\t'; if (r.hap == -1) *p++ = '*'; else p = fmt_i32(p, (int32_t)r.hap); }
+            }
+            *p++ = '\n';
+            if (p >= flush_at) { fwrite(buf.data(), 1, (size_t)(p - buf.data()), fp); p = buf.data(); }
         }
     }
+    if (p != buf.data()) fwrite(buf.data(), 1, (size_t)(p - buf.data()), fp);
 }
 
 void print_view_records(FILE *fp, const OutOpts &o, const std::vector<std::string> &names, const mmc_batch_t *batch,
                         const BatchMeta &meta, const mmc_view_rec_t *recs, uint64_t n, const std::vector<std::string> &codes) {
+    char prob_txt[256][16];                                          // (ml + 0.5) / 256 has 256 values: format them once
+    for (int b = 0; b < 256; ++b) { char *e = fmt_f6(prob_txt[b], (double)((b + 0.5) / 256.0)); *e = 0; }
     for (uint64_t i = 0; i < n; ++i) {                               // src/mod.c:595-616
         const mmc_view_rec_t &v = recs[i];
         int32_t tid = batch->tid[v.read];
         const char *tname = tid >= 0 && (size_t)tid < names.size() ? names[tid].c_str() : "*";
-        double p = (double)((v.mod_prob + 0.5) / 256.0);
-        fprintf(fp, "%s\t%d\t%c\t%s\t%d\t%s\t%f", tname, v.ref_pos, v.strand ? '-' : '+', meta.qname(v.read), v.read_pos,
-                codes[v.code].c_str(), p);
+        fprintf(fp, "%s\t%d\t%c\t%s\t%d\t%s\t%s", tname, v.ref_pos, v.strand ? '-' : '+', meta.qname(v.read), v.read_pos,
+                codes[v.code].c_str(), prob_txt[v.mod_prob]);
         if (o.insertions) fprintf(fp, "\t%d", (int)v.ins_offset);
         if (o.haplotypes) fprintf(fp, "\t%d", (int)v.hp);
         fputc('\n', fp);
