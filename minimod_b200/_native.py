@@ -127,6 +127,8 @@ def _declare_host(lib):
     vp, P = C.c_void_p, C.POINTER
     sig = {
         "mmh_bam_open": (vp, [C.c_char_p, C.c_char_p, C.c_int]),
+        "mmh_bam_open_t": (vp, [C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
+        "mmh_bam_scan": (C.c_longlong, [vp, P(C.c_ulonglong)]),
         "mmh_bam_close": (None, [vp]),
         "mmh_bam_n_targets": (C.c_int, [vp]),
         "mmh_bam_target_name": (C.c_char_p, [vp, C.c_int]),

@@ -1,28 +1,178 @@
 #include "bam.h"
 #include <string.h>
+#include <algorithm>
 
 namespace mmh {
 
 static inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 static inline uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | p[1] << 8); }
 
-BamFile::~BamFile() { if (gz_) gzclose(gz_); }
+// ---------------------------------------------------------------------------------------------------------
+// BGZF: gzip member = 12-byte header (XLEN at 10) + extra field with subfield 'B','C',2,BSIZE + raw deflate
+// + CRC32 + ISIZE; BSIZE + 1 is the size of the whole member (SAM spec 4.1).
+// ---------------------------------------------------------------------------------------------------------
+static const size_t kRing = 256;
 
-bool BamFile::read_exact(void *buf, size_t n) {
-    uint8_t *p = (uint8_t *)buf;
-    while (n) {
-        unsigned chunk = n > (1u << 30) ? (1u << 30) : (unsigned)n;
-        int got = gzread(gz_, p, chunk);
-        if (got <= 0) return false;
-        p += got; n -= (size_t)got;
-    }
+bool BgzfReader::is_bgzf(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    uint8_t h[18];
+    const bool ok = fread(h, 1, 18, f) == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && le16(h + 10) >= 6 &&
+                    h[12] == 'B' && h[13] == 'C' && le16(h + 14) == 2;
+    fclose(f);
+    return ok;
+}
+
+bool BgzfReader::open(const std::string &path, int threads) {
+    fp_ = fopen(path.c_str(), "rb");
+    if (!fp_) return false;
+    ring_.resize(kRing);
+    if (threads < 1) threads = 1;
+    threads_.emplace_back(&BgzfReader::producer, this);
+    for (int i = 0; i < threads; ++i) threads_.emplace_back(&BgzfReader::worker, this);
     return true;
 }
 
-bool BamFile::open(const std::string &path, std::string *err) {
-    gz_ = gzopen(path.c_str(), "rb");
-    if (!gz_) { if (err) *err = "cannot open " + path; return false; }
-    gzbuffer(gz_, 4u << 20);
+BgzfReader::~BgzfReader() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto &t : threads_) t.join();
+    if (fp_) fclose(fp_);
+}
+
+void BgzfReader::producer() {
+    std::vector<uint8_t> hdr(18);
+    for (;;) {
+        Slot *s;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || ring_[produced_ % kRing].st == EMPTY; });
+            if (stop_) return;
+            s = &ring_[produced_ % kRing];
+        }
+        bool bad = false, end = false;
+        size_t got = fread(hdr.data(), 1, 18, fp_);
+        if (got == 0) end = true;
+        else if (got != 18 || hdr[0] != 0x1f || hdr[1] != 0x8b || hdr[2] != 8 || !(hdr[3] & 4)) bad = true;
+        else {
+            // find the BC subfield (it is the first one in every BGZF writer, but the spec allows others)
+            const size_t xlen = le16(hdr.data() + 10);
+            std::vector<uint8_t> extra(xlen);
+            memcpy(extra.data(), hdr.data() + 12, 6);
+            if (xlen < 6 || (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, fp_) != xlen - 6)) bad = true;
+            size_t bsize = 0;
+            for (size_t o = 0; !bad && o + 4 <= xlen;) {
+                const size_t slen = le16(extra.data() + o + 2);
+                if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2 && o + 6 <= xlen) { bsize = (size_t)le16(extra.data() + o + 4) + 1; break; }
+                o += 4 + slen;
+            }
+            if (!bad && (bsize < 12 + xlen + 8)) bad = true;
+            if (!bad) {
+                const size_t rest = bsize - 12 - xlen;                              // deflate data + CRC32 + ISIZE
+                s->in.resize(rest);
+                if (fread(s->in.data(), 1, rest, fp_) != rest) bad = true;
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (end) { eof_ = true; cv_.notify_all(); return; }
+            s->bad = bad; s->st = FILLED;
+            ++produced_;
+            if (bad) { eof_ = true; cv_.notify_all(); return; }
+        }
+        cv_.notify_all();
+    }
+}
+
+void BgzfReader::worker() {
+    z_stream zs;
+    for (;;) {
+        Slot *s;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || (claimed_ < produced_ && ring_[claimed_ % kRing].st == FILLED) || (eof_ && claimed_ == produced_); });
+            if (stop_ || (eof_ && claimed_ == produced_)) return;
+            s = &ring_[claimed_ % kRing];
+            s->st = BUSY;
+            ++claimed_;
+        }
+        bool bad = s->bad;
+        size_t out_len = 0;
+        if (!bad) {
+            const size_t n = s->in.size();
+            const uint32_t isize = le32(s->in.data() + n - 4), crc = le32(s->in.data() + n - 8);
+            s->out.resize(isize ? isize : 1);
+            memset(&zs, 0, sizeof zs);
+            if (isize > (1u << 16) || inflateInit2(&zs, -15) != Z_OK) bad = true;
+            else {
+                zs.next_in = s->in.data(); zs.avail_in = (uInt)(n - 8);
+                zs.next_out = s->out.data(); zs.avail_out = (uInt)isize;
+                const int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+                if (rc != Z_STREAM_END || zs.total_out != isize) bad = true;
+                inflateEnd(&zs);
+                if (!bad && isize && (uint32_t)crc32(crc32(0L, Z_NULL, 0), s->out.data(), (uInt)isize) != crc) bad = true;
+                out_len = isize;
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            s->bad = bad; s->out_len = out_len; s->st = DONE;
+        }
+        cv_.notify_all();
+    }
+}
+
+long BgzfReader::read(void *buf, size_t n) {
+    uint8_t *p = (uint8_t *)buf;
+    size_t done = 0;
+    while (done < n) {
+        Slot *s;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return ring_[consumed_ % kRing].st == DONE || (eof_ && consumed_ == produced_); });
+            if (ring_[consumed_ % kRing].st != DONE) break;                         // end of file
+            s = &ring_[consumed_ % kRing];
+        }
+        if (s->bad) return -1;
+        const size_t take = std::min(n - done, s->out_len - cur_off_);
+        memcpy(p + done, s->out.data() + cur_off_, take);
+        done += take; cur_off_ += take;
+        if (cur_off_ == s->out_len) {
+            { std::lock_guard<std::mutex> lk(mu_); s->st = EMPTY; ++consumed_; }
+            cur_off_ = 0;
+            cv_.notify_all();
+        }
+    }
+    return (long)done;
+}
+
+BamFile::~BamFile() { if (gz_) gzclose(gz_); delete bgzf_; }
+
+long BamFile::read_some(void *buf, size_t n) {
+    if (bgzf_) return bgzf_->read(buf, n);
+    size_t done = 0;
+    uint8_t *p = (uint8_t *)buf;
+    while (done < n) {
+        unsigned chunk = n - done > (1u << 30) ? (1u << 30) : (unsigned)(n - done);
+        int got = gzread(gz_, p + done, chunk);
+        if (got < 0) return -1;
+        if (got == 0) break;
+        done += (size_t)got;
+    }
+    return (long)done;
+}
+
+bool BamFile::read_exact(void *buf, size_t n) { return read_some(buf, n) == (long)n; }
+
+bool BamFile::open(const std::string &path, std::string *err, int threads) {
+    if (BgzfReader::is_bgzf(path)) {
+        bgzf_ = new BgzfReader();
+        if (!bgzf_->open(path, threads)) { if (err) *err = "cannot open " + path; return false; }
+    } else {
+        gz_ = gzopen(path.c_str(), "rb");
+        if (!gz_) { if (err) *err = "cannot open " + path; return false; }
+        gzbuffer(gz_, 4u << 20);
+    }
     uint8_t b4[4];
     if (!read_exact(b4, 4) || memcmp(b4, "BAM\1", 4) != 0) { if (err) *err = path + " is not a BAM file"; return false; }
     if (!read_exact(b4, 4)) { if (err) *err = "truncated BAM header"; return false; }
@@ -45,7 +195,7 @@ bool BamFile::open(const std::string &path, std::string *err) {
 
 int BamFile::next(BamRecord *r) {
     uint8_t b4[4], fx[32];
-    int got = gzread(gz_, b4, 4);
+    long got = read_some(b4, 4);
     if (got == 0) return 0;
     if (got != 4) return -1;
     uint32_t block = le32(b4);

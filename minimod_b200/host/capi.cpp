@@ -36,6 +36,23 @@ void *mmh_bam_open(const char *path, char *err, int errlen) {
     if (!b->open(path, &e)) { set_err(err, errlen, e); delete b; return nullptr; }
     return b;
 }
+// the same with an explicit number of BGZF inflate threads (hts_set_threads equivalent)
+void *mmh_bam_open_t(const char *path, int threads, char *err, int errlen) {
+    BamFile *b = new BamFile();
+    std::string e;
+    if (!b->open(path, &e, threads)) { if (err && errlen > 0) snprintf(err, errlen, "%s", e.c_str()); delete b; return nullptr; }
+    return b;
+}
+// read every record (ingest throughput measurements): returns the number of records, -1 on a corrupt file
+long long mmh_bam_scan(void *h, unsigned long long *bytes) {
+    BamFile *b = (BamFile *)h;
+    BamRecord r;
+    long long n = 0;
+    unsigned long long tot = 0;
+    for (;;) { int rc = b->next(&r); if (rc == 0) break; if (rc < 0) return -1; ++n; tot += (unsigned long long)r.l_data + 36; }
+    if (bytes) *bytes = tot;
+    return n;
+}
 void mmh_bam_close(void *h) { delete (BamFile *)h; }
 int mmh_bam_n_targets(void *h) { return (int)((BamFile *)h)->names.size(); }
 const char *mmh_bam_target_name(void *h, int i) { return ((BamFile *)h)->names[i].c_str(); }

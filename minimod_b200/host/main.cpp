@@ -184,7 +184,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
 
     // ---- BAM header first: the device context is sized from the contig table
     BamFile bam;
-    if (!bam.open(bam_file, &err)) { ERROR("%s", err.c_str()); exit(EXIT_FAILURE); }
+    if (!bam.open(bam_file, &err, opt.num_thread)) { ERROR("%s", err.c_str()); exit(EXIT_FAILURE); }
     std::vector<const char *> names;
     for (const std::string &n : bam.names) names.push_back(n.c_str());
 

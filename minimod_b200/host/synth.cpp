@@ -315,20 +315,57 @@ int64_t mmh_synth_fill(void *h, mmc_batch_t *b, uint64_t first, uint64_t count, 
     return (int64_t)done;
 }
 
-// Write reads [first, first+count) as a BAM (BGZF with stored blocks; level 0 keeps it fast).
+namespace {
+// Minimal BGZF writer (SAM spec 4.1): 0xff00-byte blocks, raw deflate level 1, 'BC' extra field, EOF marker.
+struct BgzfWriter {
+    FILE *fp = nullptr;
+    std::vector<uint8_t> buf, out;
+    bool open(const char *path) { fp = fopen(path, "wb"); buf.reserve(0xff00); out.resize(0x10000 + 1024); return fp != nullptr; }
+    void block(const uint8_t *p, size_t n) {
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = const_cast<uint8_t *>(p); zs.avail_in = (uInt)n;
+        zs.next_out = out.data() + 18; zs.avail_out = (uInt)(out.size() - 18 - 8);
+        deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        memcpy(out.data(), hdr, 16);
+        const uint16_t bsize = (uint16_t)(18 + clen + 8 - 1);
+        memcpy(out.data() + 16, &bsize, 2);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, (uInt)n), isize = (uint32_t)n;
+        memcpy(out.data() + 18 + clen, &crc, 4); memcpy(out.data() + 18 + clen + 4, &isize, 4);
+        fwrite(out.data(), 1, 18 + clen + 8, fp);
+    }
+    void write(const void *p, size_t n) {
+        const uint8_t *q = (const uint8_t *)p;
+        while (n) {
+            const size_t take = std::min(n, (size_t)0xff00 - buf.size());
+            buf.insert(buf.end(), q, q + take); q += take; n -= take;
+            if (buf.size() == 0xff00) { block(buf.data(), buf.size()); buf.clear(); }
+        }
+    }
+    void close() {
+        if (!buf.empty()) { block(buf.data(), buf.size()); buf.clear(); }
+        block(nullptr, 0);                                                          // EOF marker: an empty block
+        fclose(fp); fp = nullptr;
+    }
+};
+}  // namespace
+
+// Write reads [first, first+count) as a BAM in BGZF blocks (deflate level 1 keeps it fast).
 int mmh_synth_write_bam(void *h, const char *path, uint64_t first, uint64_t count, int n_threads, mmh_synth_stats_t *st) {
     Synth *s = (Synth *)h;
     if (first + count > s->n_reads) count = s->n_reads > first ? s->n_reads - first : 0;
-    gzFile gz = gzopen(path, "wb1");
-    if (!gz) return -1;
-    gzbuffer(gz, 4u << 20);
-    auto w32 = [&](uint32_t v) { gzwrite(gz, &v, 4); };
-    gzwrite(gz, "BAM\1", 4);
+    BgzfWriter gz;
+    if (!gz.open(path)) return -1;
+    auto w32 = [&](uint32_t v) { gz.write(&v, 4); };
+    gz.write("BAM\1", 4);
     std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
     for (auto &c : s->contigs) text += "@SQ\tSN:" + c.name + "\tLN:" + std::to_string(c.seq.size()) + "\n";
-    w32((uint32_t)text.size()); gzwrite(gz, text.data(), (unsigned)text.size());
+    w32((uint32_t)text.size()); gz.write(text.data(), text.size());
     w32((uint32_t)s->contigs.size());
-    for (auto &c : s->contigs) { w32((uint32_t)c.name.size() + 1); gzwrite(gz, c.name.c_str(), (unsigned)c.name.size() + 1); w32((uint32_t)c.seq.size()); }
+    for (auto &c : s->contigs) { w32((uint32_t)c.name.size() + 1); gz.write(c.name.c_str(), c.name.size() + 1); w32((uint32_t)c.seq.size()); }
     if (n_threads < 1) n_threads = 1;
     const uint64_t chunk = 256;
     std::vector<BamRecord> recs(chunk * (uint64_t)n_threads);
@@ -349,13 +386,13 @@ int mmh_synth_write_bam(void *h, const char *path, uint64_t first, uint64_t coun
             uint16_t nc = (uint16_t)r.n_cigar; memcpy(fx + 16, &nc, 2); memcpy(fx + 18, &r.flag, 2);
             memcpy(fx + 20, &r.l_qseq, 4);
             int32_t m1 = -1, z = 0; memcpy(fx + 24, &m1, 4); memcpy(fx + 28, &m1, 4); memcpy(fx + 32, &z, 4);
-            gzwrite(gz, fx, 36);
-            gzwrite(gz, r.data.data(), (unsigned)r.l_data);
+            gz.write(fx, 36);
+            gz.write(r.data.data(), (size_t)r.l_data);
             add_stats(r, st);
         }
         done += n;
     }
-    gzclose(gz);
+    gz.close();
     return 0;
 }
 
