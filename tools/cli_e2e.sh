@@ -16,10 +16,11 @@ st = s.write_bam("$D/reads.bam", first, $N, threads=$T)
 print("wrote", st["n_reads"], "reads,", st["bases"] // 1000000, "Mbase")
 PY
 ls -la $D | tail -2
+wall() { local t0=$(date +%s.%N); "$@"; local t1=$(date +%s.%N); echo "$(echo "$t1 - $t0" | python -c "print('%.2f' % eval(input()))") s wall"; }
 for i in 1 2; do
-  /usr/bin/time -f "minimod-b200 freq -b: %e s wall, %U s user" minimod_b200/bin/minimod freq -c "m[CG]" -m 0.8 -b -t $T -K 4092 -B 100M -o $D/mine.bed $D/ref.fa $D/reads.bam 2> $D/mine.err; tail -1 $D/mine.err
+  echo -n "minimod-b200 freq -b (run $i): "; wall minimod_b200/bin/minimod freq -c "m[CG]" -m 0.8 -b -t $T -K 4092 -B 100M -o $D/mine.bed $D/ref.fa $D/reads.bam 2> $D/mine.err
 done
-/usr/bin/time -f "minimod_ref   freq -b: %e s wall, %U s user" oracle/_ref/minimod_ref freq -c "m[CG]" -m 0.8 -b -t $T -K 4092 -B 100M -o $D/ref.bed $D/ref.fa $D/reads.bam 2> $D/ref.err; tail -1 $D/ref.err
+echo -n "minimod_ref   freq -b: "; wall oracle/_ref/minimod_ref freq -c "m[CG]" -m 0.8 -b -t $T -K 4092 -B 100M -o $D/ref.bed $D/ref.fa $D/reads.bam 2> $D/ref.err
 grep -E "Data loading time|Data processing time|Data merging time|Data output time|Sorting" $D/ref.err | sed 's/^/  ref: /'
 grep -E "time|GPU" $D/mine.err | tail -8 | sed 's/^/  mine: /'
 cmp $D/mine.bed $D/ref.bed && echo "outputs byte-identical ($(wc -l < $D/mine.bed) rows)"
