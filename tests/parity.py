@@ -25,8 +25,10 @@ class Pair:
         self.subtool = N.MMC_FREQ if subtool == "freq" else N.MMC_VIEW
         self.mods, self.n_mods = make_mods(codes, thresh, self.subtool)
         self.contigs = contigs
-        names = (C.c_char_p * len(contigs))(*[n.encode() for n, _ in contigs])
-        lens = (C.c_uint32 * len(contigs))(*[len(s) if s is not None else 1000 for _, s in contigs])
+        # entries: (name, sequence) or (name, None, length) for a header contig whose reference is not loaded here
+        contigs = [(c[0], c[1], len(c[1]) if c[1] is not None else (c[2] if len(c) > 2 else 1000)) for c in contigs]
+        names = (C.c_char_p * len(contigs))(*[c[0].encode() for c in contigs])
+        lens = (C.c_uint32 * len(contigs))(*[c[2] for c in contigs])
         o = N.MmcOpts()
         o.struct_size = C.sizeof(N.MmcOpts)
         o.subtool, o.n_mods, o.mods = self.subtool, self.n_mods, self.mods
@@ -38,7 +40,7 @@ class Pair:
         assert lib.mmc_create(C.byref(self.ctx), C.byref(o), len(contigs), names, lens) == 0, lib.mmc_strerror(None)
         th = (C.c_double * self.n_mods)(*oracle_port.parse_thresholds(thresh, self.n_mods))
         self.octx = self.O.oracle_create(self.subtool, self.n_mods, self.mods, th, int(insertions), int(haplotypes), len(contigs), lens)
-        for tid, (_, s) in enumerate(contigs):
+        for tid, (_, s, _n) in enumerate(contigs):
             if s is None:
                 continue
             sb = s if isinstance(s, bytes) else s.encode()

@@ -80,3 +80,66 @@ def test_region_sharding_two_ranks_gloo(emul_lib, tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e.decode()[-3000:]
     assert b"OK" in outs[0][0]
+
+
+# ---- contig sharding (BASELINE config 5 shape): GRCh38-like contig table scaled down, contigs dealt to ranks by LPT,
+# every rank loads the reference and allocates counts for ITS contigs only and sees only their reads; no collective.
+CONTIG_WORKER = r'''
+import ctypes as C, os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch.distributed as dist
+from minimod_b200 import _native as N, shard
+from minimod_b200.synth import Synth
+from parity import Pair
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+lib = N.load_cuda(os.path.join({root!r}, "tests/kernel_emul/_build/libminimod_emul.so"))
+lens = {lens!r}
+contigs = tuple(("ctg%d" % i, l) for i, l in enumerate(lens))
+s = Synth(5, contigs=contigs, coverage=1.5)
+refs = []
+for tid in range(len(contigs)):
+    p, n = s.ref(tid); refs.append(C.string_at(p, n))
+bins, load = shard.lpt_partition(lens, world)
+mine = set(bins[rank])
+kw = dict(max_reads=s.n_reads + 8, max_bytes=64 << 20)
+full = Pair(lib, "freq", [(contigs[t][0], refs[t]) for t in range(len(contigs))], "m[CG]", "0.8", **kw)
+s.fill(full.batch, 0, s.n_reads, 2)
+tids = [full.batch.contents.tid[i] for i in range(full.batch.contents.n_reads)]
+pair = Pair(lib, "freq", [(contigs[t][0], refs[t] if t in mine else None, lens[t]) for t in range(len(contigs))], "m[CG]", "0.8", **kw)
+n_mine = 0
+for t in sorted(mine):                                     # reads are sorted by contig: one contiguous range each
+    idx = [i for i, x in enumerate(tids) if x == t]
+    if not idx: continue
+    assert idx == list(range(idx[0], idx[-1] + 1))
+    b = pair.batch.contents                                # the packer appends: start every batch empty
+    b.n_reads = 0; b.cigar_used = 0; b.seq_used = 0; b.mm_used = 0; b.ml_used = 0
+    got, _ = s.fill(pair.batch, idx[0], len(idx), 2); assert got == len(idx)
+    rc, msg = pair.run_device(); assert rc == 0, msg
+    n_mine += len(idx)
+rows = pair.device_freq()
+assert all(r[0] in mine for r in rows)
+gathered = [None] * world
+dist.all_gather_object(gathered, (rows, n_mine))
+if rank == 0:
+    rc, msg = full.run_device(); assert rc == 0, msg
+    single = full.device_freq()
+    merged = sorted(r for part, _ in gathered for r in part)
+    assert sum(n for _, n in gathered) == s.n_reads
+    assert merged == single and len(single) > 500, (len(merged), len(single))
+    print("OK", len(single), "rows over", len(lens), "contigs; reads per rank", [n for _, n in gathered])
+dist.destroy_process_group()
+'''
+
+
+def test_contig_sharding_two_ranks_gloo(emul_lib, tmp_path):
+    lens = [max(3000, l // 3000) for l in GRCH38_LIKE[:25]] + [3000 + 40 * i for i in range(20)]
+    script = tmp_path / "contig_worker.py"
+    script.write_text(CONTIG_WORKER.format(root=ROOT, lens=lens))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29627", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+             for r in range(2)]
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e.decode()[-3000:]
+    assert b"OK" in outs[0][0]
