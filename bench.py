@@ -71,14 +71,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, more=()):
+        """Samples taken inside [t0,t1] or any (a,b) of `more` (the timed regions; the GPU idles in between)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        wins = [(t0, t1)] + list(more)
+        rows = [r for t, r in self.rows if any(a - 0.05 <= t <= b + 0.15 for a, b in wins)] or [r for _, r in self.rows]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             try:
@@ -262,7 +264,6 @@ def main():
         kernel_ms.append(ms.value)
     barrier()
     t1 = time.time()
-    clocks = sampler.stop(t0, t1) if sampler else None
     tm1 = N.MmcTimers(); lib.mmc_get_timers(ctxA, C.byref(tm1))
     launches = int(tm1.kernel_launches - tm0.kernel_launches)
     wall = t1 - t0
@@ -307,6 +308,7 @@ def main():
         rows_e2e = e2e_step()
     barrier()
     te1 = time.time()
+    clocks = sampler.stop(t0, t1, more=[(te0, te1)]) if sampler else None   # both timed regions (value, e2e)
     tmB = N.MmcTimers(); lib.mmc_get_timers(ctxB, C.byref(tmB))
     assert rows_e2e == n_rows, (rows_e2e, n_rows)
     e2e_wall = te1 - te0
