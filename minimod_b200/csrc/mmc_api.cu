@@ -55,6 +55,7 @@ struct Slot {
     std::vector<mmc_view_rec_t> view_out;
     bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false;
     uint32_t n_reads_submitted = 0;
+    uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
 };
 
 struct ContigHost {
@@ -225,6 +226,34 @@ Slot *slot_of(mmc_ctx *ctx, mmc_batch_t *b) {
     return nullptr;
 }
 
+// Shape of the batch a slot holds: sizes the scratch and picks the k_decode_warp variant.  Runs at upload time so
+// that re-launching an HBM-resident batch costs no host work.
+void analyse_batch(mmc_ctx *ctx, Slot &s) {
+    const mmc_batch_t &b = s.pub;
+    const uint32_t n = b.n_reads;
+    uint32_t max_cig = 0, max_l = 0;
+    uint64_t pool_need = 0;                    // split path: words of scratch for every read's dir | cq | cr
+    std::vector<uint32_t> &need = ctx->need_tmp;   // per read: arena words for un-sampled CIGAR arrays + rank index
+    need.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
+        max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
+        const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
+        pool_need += 164 + 2ull * nc + 8;
+        need[i] = (uint32_t)std::min<uint64_t>(0xffffffffu, (L >> 8) + 2 + nc / 2 + n_u4 + 2 + (L >> 6) + 2 + 12);   // CIGAR sampled 1:4 at worst
+    }
+    // variant for this batch: the most CTAs per SM whose arena holds ~95% of the reads with an un-sampled index
+    int mb = ctx->w_minb;
+    if (!ctx->w_pinned && n > 0) {
+        const size_t k = (size_t)((uint64_t)(n - 1) * 95 / 100);
+        std::nth_element(need.begin(), need.begin() + k, need.end());
+        const uint32_t p95 = need[k];
+        mb = 3;
+        while (mb > 1 && (ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed)) / 4u < p95) --mb;
+    }
+    s.max_cig = max_cig; s.max_l = max_l; s.pool_need = pool_need; s.variant = mb;
+}
+
 int upload(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const size_t n = b.n_reads;
@@ -247,6 +276,7 @@ int upload(mmc_ctx *ctx, Slot &s) {
     ctx->tm.h2d_bytes += bytes;
     s.uploaded = true; s.h2d_pending = true;
     s.n_reads_submitted = (uint32_t)n;
+    analyse_batch(ctx, s);
     return MMC_OK;
 }
 
@@ -261,26 +291,10 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 64, cudaMemcpyHostToDevice, s.stream));
     if (n == 0) { s.in_flight = true; s.timed = false; return MMC_OK; }
 
-    uint32_t max_cig = 0, max_l = 0;
-    uint64_t pool_need = 0;                    // split path: words of scratch for every read's dir | cq | cr
-    std::vector<uint32_t> &need = ctx->need_tmp;   // per read: arena words for un-sampled CIGAR arrays + rank index
-    need.resize(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
-        max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
-        const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
-        pool_need += 164 + 2ull * nc + 8;
-        need[i] = (uint32_t)std::min<uint64_t>(0xffffffffu, (L >> 8) + 2 + nc / 2 + n_u4 + 2 + (L >> 6) + 2 + 12);   // CIGAR sampled 1:4 at worst
-    }
-    // variant for this batch: the most CTAs per SM whose arena holds ~95% of the reads with an un-sampled index
-    int mb = ctx->w_minb;
-    if (!ctx->w_pinned && n > 0) {
-        const size_t k = (size_t)((uint64_t)(n - 1) * 95 / 100);
-        std::nth_element(need.begin(), need.begin() + k, need.end());
-        const uint32_t p95 = need[k];
-        mb = 3;
-        while (mb > 1 && (ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed)) / 4u < p95) --mb;
-    }
+    // shape of the batch, computed once per upload (analyse_batch)
+    const uint32_t max_cig = s.max_cig, max_l = s.max_l;
+    const uint64_t pool_need = s.pool_need;
+    const int mb = s.variant;
     const uint32_t w_arena_bytes = ctx->wv_arena[mb], setup_arena_bytes = ctx->wv_setup_arena[mb];
     unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * ctx->ctas_per_sm);
     if (grid == 0) grid = 1;
