@@ -12,12 +12,18 @@
 
 #include <algorithm>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/minimod_cuda.h"
 #include "mmc_device.cuh"
 #include "mmc_decode_warp.cuh"
 #include "mmc_decode_flat.cuh"
+#include "mmc_sparse.cuh"
+#ifndef MMC_EMUL
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#endif
 
 using namespace mmc;
 
@@ -80,7 +86,7 @@ struct mmc_ctx {
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
     // [0] unused; chosen per batch from the reads' sizes unless MMC_WARP_OCC pins one.
-    uint32_t wv_arena[5] = {0, 28672u, 14208u, 9344u, 6912u};   // (228 KB / MINB - 1 KB - LUTs) / 8 warps
+    uint32_t wv_arena[5] = {0, 28672u, 14192u, 9328u, 6896u};   // (228 KB / MINB - 1 KB - kWHeadBytes) / 8 warps
     uint32_t wv_setup_arena[5] = {0, 0, 0, 0, 0};               // k_flat_setup: WRead + room for dir | cq | cr
     int wv_ctas[5] = {0, 1, 1, 1, 1};
     int w_pinned = 0;                          // MMC_WARP_OCC / MMC_WARP_ARENA given: no per-batch choice
@@ -103,11 +109,16 @@ struct mmc_ctx {
     uint32_t *d_tile_count = nullptr; unsigned long long *d_tile_off = nullptr, *d_totals = nullptr;
     size_t fin_tiles_cap = 0, fin_jobs_cap = 0;
     FreqRecDev *d_rows = nullptr; size_t d_rows_cap = 0;
+    // device-side finalize of the sparse side buffer (mmc_sparse.cuh): grow-only scratch
+    uint64_t sparse_dev_min = 1u << 16;                              // fewer records than this: host sort (a few ms at most)
+    void *d_sp_scratch = nullptr; size_t sp_scratch_cap = 0;         // keys, indexes, flags, offsets, sort temp
+    FreqRecDev *d_srows = nullptr; size_t d_srows_cap = 0;           // reduced sparse rows
+    FreqRecDev *d_merged = nullptr; size_t d_merged_cap = 0;         // dense + sparse rows in output order
+    unsigned long long *d_sn_rows = nullptr, *h_sn_rows = nullptr;   // number of reduced sparse rows (device, pinned)
     mmc_freq_rec_t *h_rows = nullptr; size_t h_rows_cap = 0;       // pinned
     unsigned long long *h_totals = nullptr;                        // pinned, fin_jobs_cap entries
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
     // results
-    std::vector<mmc_freq_rec_t> freq_out;
     std::vector<uint32_t> need_tmp;
     std::vector<std::string> code_names;
     mmc_timers_t tm{};
@@ -361,7 +372,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         const uint64_t warps = n;                             // one warp per read, persistent above the resident limit
         unsigned wgrid = (unsigned)std::min<uint64_t>((warps + kWThreads / 32 - 1) / (kWThreads / 32), (uint64_t)ctx->sm_count * ctx->wv_ctas[mb]);
         if (wgrid == 0) wgrid = 1;
-        const size_t wsmem = (size_t)kWLutSlots * 256 + (size_t)w_arena_bytes * (kWThreads / 32);
+        const size_t wsmem = (size_t)kWHeadBytes + (size_t)w_arena_bytes * (kWThreads / 32);
         PreParams Q; Q.reads = nullptr; Q.n = 0;
         if (ctx->split_path) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
@@ -369,7 +380,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
             F.consumer_flex_words = (w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
             F.read_count = n;
             const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
-            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWLutSlots * 256 + (size_t)setup_arena_bytes * (kFThreads / 32), s.stream, P, F);
+            MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWHeadBytes + (size_t)setup_arena_bytes * (kFThreads / 32), s.stream, P, F);
             CU(ctx, cudaGetLastError());
             ctx->tm.kernel_launches += 1;
             Q.reads = s.d_reads; Q.n = n;
@@ -472,6 +483,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         else if (!strcmp(e, "split")) ctx->split_path = 1;
     }
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
+    if (const char *e = getenv("MMC_SPARSE_DEVICE_MIN")) ctx->sparse_dev_min = strtoull(e, nullptr, 10);   // test hook: 0 = always sort sparse records on the device
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
         long v = atol(e);
         if (v >= (long)sizeof(WFixed) + 256 && v <= 28 * 1024) { ctx->wv_arena[ctx->w_minb] = (uint32_t)(v & ~15l); ctx->w_pinned = 1; }
@@ -500,11 +512,11 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     ctx->ctas_per_sm = occ < 1 ? 1 : occ;
     {
         size_t setup_max = 0;
-        for (int mb = 1; mb <= 4; ++mb) setup_max = std::max(setup_max, (size_t)kWLutSlots * 256 + (size_t)ctx->wv_setup_arena[mb] * (kFThreads / 32));
+        for (int mb = 1; mb <= 4; ++mb) setup_max = std::max(setup_max, (size_t)kWHeadBytes + (size_t)ctx->wv_setup_arena[mb] * (kFThreads / 32));
         CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)setup_max));
 #define MMC_WARP_ATTR(MB)                                                                                                        \
         do {                                                                                                                     \
-            const size_t smem = (size_t)kWLutSlots * 256 + (size_t)ctx->wv_arena[MB] * (kWThreads / 32);                         \
+            const size_t smem = (size_t)kWHeadBytes + (size_t)ctx->wv_arena[MB] * (kWThreads / 32);                         \
             int wocc = 1;                                                                                                        \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
             CUC(cudaFuncSetAttribute((k_decode_warp<MB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
@@ -638,6 +650,11 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (ctx->d_tile_off) cudaFree(ctx->d_tile_off);
     if (ctx->d_totals) cudaFree(ctx->d_totals);
     if (ctx->d_rows) cudaFree(ctx->d_rows);
+    if (ctx->d_sp_scratch) cudaFree(ctx->d_sp_scratch);
+    if (ctx->d_srows) cudaFree(ctx->d_srows);
+    if (ctx->d_merged) cudaFree(ctx->d_merged);
+    if (ctx->d_sn_rows) cudaFree(ctx->d_sn_rows);
+    if (ctx->h_sn_rows) cudaFreeHost(ctx->h_sn_rows);
     if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     if (ctx->ev_d0) cudaEventDestroy(ctx->ev_d0);
@@ -832,6 +849,97 @@ static int refresh_code_names(mmc_ctx *ctx) {
     return MMC_OK;
 }
 
+}  // extern "C"
+
+// ---- the two library primitives of the sparse finalize: stable LSD radix sort of (key, value) pairs, exclusive sum.
+// Under the SIMT emulator (CPU CI) device memory is host memory and the same contracts are met with the C++ library.
+template <typename K>
+static int sort_pairs(mmc_ctx *ctx, const K *kin, K *kout, const uint32_t *vin, uint32_t *vout, uint32_t n, int end_bit, void *tmp, size_t tmp_bytes) {
+#ifdef MMC_EMUL
+    (void)tmp; (void)tmp_bytes; (void)ctx;
+    std::vector<uint32_t> ord(n);
+    for (uint32_t i = 0; i < n; ++i) ord[i] = i;
+    const K mask = end_bit >= (int)(8 * sizeof(K)) ? ~(K)0 : (((K)1 << end_bit) - 1);
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return (kin[x] & mask) < (kin[y] & mask); });
+    for (uint32_t i = 0; i < n; ++i) { kout[i] = kin[ord[i]]; vout[i] = vin[ord[i]]; }
+#else
+    CU(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, ctx->fin_stream));
+#endif
+    return MMC_OK;
+}
+static int exclusive_sum(mmc_ctx *ctx, const uint32_t *in, uint32_t *out, uint32_t n, void *tmp, size_t tmp_bytes) {
+#ifdef MMC_EMUL
+    (void)tmp; (void)tmp_bytes; (void)ctx;
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < n; ++i) { const uint32_t v = in[i]; out[i] = acc; acc += v; }
+#else
+    CU(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, out, (int)n, ctx->fin_stream));
+#endif
+    return MMC_OK;
+}
+
+// Sort + reduce the sn records of the sparse side buffer into ctx->d_srows (row order), count into ctx->h_sn_rows
+// (valid after the next synchronize of fin_stream).  Everything is queued on fin_stream.
+static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn) {
+    const uint32_t n = (uint32_t)sn;
+    size_t tmp_bytes = 0;
+#ifndef MMC_EMUL
+    {
+        size_t t1 = 0, t2 = 0, t3 = 0;
+        CU(ctx, cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 25, ctx->fin_stream));
+        CU(ctx, cub::DeviceRadixSort::SortPairs(nullptr, t2, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, 0, 64, ctx->fin_stream));
+        CU(ctx, cub::DeviceScan::ExclusiveSum(nullptr, t3, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, ctx->fin_stream));
+        tmp_bytes = std::max(t1, std::max(t2, t3));
+    }
+#endif
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b32 = up(4 * (size_t)n), b64 = up(8 * (size_t)n);
+    const size_t need = 4 * b32 + 2 * b64 + up(tmp_bytes);
+    if (need > ctx->sp_scratch_cap) {
+        if (ctx->d_sp_scratch) cudaFree(ctx->d_sp_scratch);
+        ctx->d_sp_scratch = nullptr; ctx->sp_scratch_cap = 0;
+        CU(ctx, cudaMalloc(&ctx->d_sp_scratch, need + need / 8));
+        ctx->sp_scratch_cap = need + need / 8;
+    }
+    if (sn > ctx->d_srows_cap) {
+        if (ctx->d_srows) cudaFree(ctx->d_srows);
+        ctx->d_srows = nullptr; ctx->d_srows_cap = 0;
+        CU(ctx, cudaMalloc((void **)&ctx->d_srows, sizeof(FreqRecDev) * (sn + sn / 8)));
+        ctx->d_srows_cap = sn + sn / 8;
+    }
+    if (!ctx->d_sn_rows) {
+        CU(ctx, cudaMalloc((void **)&ctx->d_sn_rows, 8));
+        CU(ctx, cudaMallocHost((void **)&ctx->h_sn_rows, 8));
+    }
+    uint8_t *base = reinterpret_cast<uint8_t *>(ctx->d_sp_scratch);
+    uint32_t *k32a = reinterpret_cast<uint32_t *>(base), *k32b = reinterpret_cast<uint32_t *>(base + b32);
+    uint32_t *ia = reinterpret_cast<uint32_t *>(base + 2 * b32), *ib = reinterpret_cast<uint32_t *>(base + 3 * b32);
+    unsigned long long *k64a = reinterpret_cast<unsigned long long *>(base + 4 * b32), *k64b = reinterpret_cast<unsigned long long *>(base + 4 * b32 + b64);
+    void *tmp = base + 4 * b32 + 2 * b64;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + kSpThreads - 1) / kSpThreads, (uint64_t)ctx->sm_count * 8);
+    int tid_bits = 1;
+    while (((size_t)1 << tid_bits) <= ctx->contigs.size()) ++tid_bits;      // the all-ones sentinel stays the largest key
+    int rc;
+    MMC_LAUNCH(k_sparse_keys, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, n, k32a, ia);
+    CU(ctx, cudaGetLastError());
+    if ((rc = sort_pairs<uint32_t>(ctx, k32a, k32b, ia, ib, n, 25, tmp, tmp_bytes)) != MMC_OK) return rc;
+    MMC_LAUNCH(k_sparse_gather, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ib, n, k64a);
+    CU(ctx, cudaGetLastError());
+    if ((rc = sort_pairs<unsigned long long>(ctx, k64a, k64b, ib, ia, n, std::min(64, 41 + tid_bits), tmp, tmp_bytes)) != MMC_OK) return rc;
+    uint32_t *flag = k32a, *off = k32b;                                      // the minor keys are no longer needed
+    MMC_LAUNCH(k_sparse_heads, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ia, n, flag);
+    CU(ctx, cudaGetLastError());
+    if ((rc = exclusive_sum(ctx, flag, off, n, tmp, tmp_bytes)) != MMC_OK) return rc;
+    MMC_LAUNCH(k_sparse_emit, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ia, (const uint32_t *)flag,
+               (const uint32_t *)off, n, ctx->d_srows, ctx->d_sn_rows);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(ctx->h_sn_rows, ctx->d_sn_rows, 8, cudaMemcpyDeviceToHost, ctx->fin_stream));
+    ctx->tm.kernel_launches += 4;
+    return MMC_OK;
+}
+
+extern "C" {
+
 int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
     if (!ctx || !recs || !n_recs) return MMC_EINVAL;
     if (ctx->opts.subtool != MMC_FREQ) return fail(ctx, MMC_ESTATE, "mmc_freq_finalize: context was created for view");
@@ -856,8 +964,34 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
         tiles += j.n_tiles;
         jobs.push_back(j);
     }
+    // the sparse side buffer is complete once the decodes are: its size bounds the rows it can add
+    unsigned long long sn = 0;
+    CU(ctx, cudaMemcpy(&sn, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost));
+    if (sn > ctx->sparse_cap)
+        return fail(ctx, MMC_ENOMEM, "sparse count buffer overflow (%llu records > capacity %llu); raise sparse_capacity",
+                    sn, (unsigned long long)ctx->sparse_cap);
+    const bool dev_sparse = sn > 0 && sn >= ctx->sparse_dev_min && sn < 0x7fffffffull;   // many records (--insertions): sorted on the device
+    std::vector<SparseRec> raw(dev_sparse ? 0 : sn);
+    if (sn && !dev_sparse) {
+        CU(ctx, cudaMemcpyAsync(raw.data(), ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToHost, ctx->fin_stream));
+        ctx->tm.d2h_bytes += sizeof(SparseRec) * sn;
+    }
+    auto ensure_rows = [&](uint64_t rows) -> int {           // pinned result buffer: dense rows + room to merge the sparse ones in
+        if (rows <= ctx->h_rows_cap) return MMC_OK;
+        if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
+        ctx->h_rows = nullptr; ctx->h_rows_cap = 0;
+        const size_t cap = rows + rows / 8 + 1024;
+        CU(ctx, cudaMallocHost((void **)&ctx->h_rows, sizeof(mmc_freq_rec_t) * cap));
+        ctx->h_rows_cap = cap;
+        return MMC_OK;
+    };
     uint64_t n_dense = 0;
     CU(ctx, cudaEventRecord(ctx->ev_f0, ctx->fin_stream));
+    if (dev_sparse) {
+        rc = sparse_rows_on_device(ctx, sn);
+        if (rc != MMC_OK) return rc;
+        if (!tiles) CU(ctx, cudaStreamSynchronize(ctx->fin_stream));       // (else the wait for the tile totals covers it)
+    }
     if (tiles) {
         if (tiles > ctx->fin_tiles_cap) {
             if (ctx->d_tile_count) cudaFree(ctx->d_tile_count);
@@ -902,13 +1036,6 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
                 CU(ctx, cudaMalloc((void **)&ctx->d_rows, sizeof(FreqRecDev) * cap));
                 ctx->d_rows_cap = cap;
             }
-            if (total > ctx->h_rows_cap) {
-                if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
-                ctx->h_rows = nullptr; ctx->h_rows_cap = 0;
-                const size_t cap = total + total / 8 + 1024;
-                CU(ctx, cudaMallocHost((void **)&ctx->h_rows, sizeof(mmc_freq_rec_t) * cap));
-                ctx->h_rows_cap = cap;
-            }
             uint64_t base = 0;
             for (size_t k = 0; k < jobs.size(); ++k) {
                 if (!ctx->h_totals[k]) continue;
@@ -918,48 +1045,59 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
                 ctx->tm.kernel_launches += 1;
                 base += ctx->h_totals[k];
             }
-            CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
-            CU(ctx, cudaEventRecord(ctx->ev_d0, ctx->fin_stream));
-            CU(ctx, cudaMemcpyAsync(ctx->h_rows, ctx->d_rows, sizeof(FreqRecDev) * total, cudaMemcpyDeviceToHost, ctx->fin_stream));
-            CU(ctx, cudaEventRecord(ctx->ev_d1, ctx->fin_stream));
-            ctx->tm.d2h_bytes += sizeof(FreqRecDev) * total;
             n_dense = total;
-        } else {
-            CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
         }
-    } else {
-        CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
     }
-    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    // rows that go back in one copy: the dense rows, with the device-sorted sparse rows merged in when there are any
+    uint64_t n_dev_rows = n_dense;
     {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->ev_f0, ctx->ev_f1) == cudaSuccess) ctx->tm.finalize_ms += ms;
-        if (n_dense && cudaEventElapsedTime(&ms, ctx->ev_d0, ctx->ev_d1) == cudaSuccess) ctx->tm.d2h_ms += ms;
-    }
-
-    // ---- sparse side buffer: sort + reduce on the host, then merge with the dense rows
-    unsigned long long sn = 0;
-    CU(ctx, cudaMemcpy(&sn, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost));
-    if (sn > ctx->sparse_cap)
-        return fail(ctx, MMC_ENOMEM, "sparse count buffer overflow (%llu records > capacity %llu); raise sparse_capacity",
-                    sn, (unsigned long long)ctx->sparse_cap);
-    std::vector<mmc_freq_rec_t> sparse;
-    if (sn) {
-        std::vector<SparseRec> raw(sn);
-        CU(ctx, cudaMemcpy(raw.data(), ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToHost));
-        ctx->tm.d2h_bytes += sizeof(SparseRec) * sn;
-        std::sort(raw.begin(), raw.end(), [](const SparseRec &x, const SparseRec &y) {
-            if (x.a != y.a) {
-                // order by tid, pos, strand, code == numeric order of a
-                return x.a < y.a;
+        const FreqRecDev *src = ctx->d_rows;
+        const uint64_t n_srows = dev_sparse ? (uint64_t)*ctx->h_sn_rows : 0;
+        if (n_srows && n_dense) {
+            n_dev_rows = n_dense + n_srows;
+            if (n_dev_rows > ctx->d_merged_cap) {
+                if (ctx->d_merged) cudaFree(ctx->d_merged);
+                ctx->d_merged = nullptr; ctx->d_merged_cap = 0;
+                const size_t cap = n_dev_rows + n_dev_rows / 8 + 1024;
+                CU(ctx, cudaMalloc((void **)&ctx->d_merged, sizeof(FreqRecDev) * cap));
+                ctx->d_merged_cap = cap;
             }
+            const unsigned grid = (unsigned)std::min<uint64_t>((n_dev_rows + kSpThreads - 1) / kSpThreads, (uint64_t)ctx->sm_count * 16);
+            MMC_LAUNCH(k_merge_rows, grid, (unsigned)kSpThreads, ctx->fin_stream, (const FreqRecDev *)ctx->d_rows, (unsigned long long)n_dense,
+                       (const FreqRecDev *)ctx->d_srows, (unsigned long long)n_srows, ctx->d_merged);
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 1;
+            src = ctx->d_merged;
+        } else if (n_srows) {
+            n_dev_rows = n_srows; src = ctx->d_srows;
+        }
+        CU(ctx, cudaEventRecord(ctx->ev_f1, ctx->fin_stream));
+        if (n_dev_rows) {
+            rc = ensure_rows(n_dev_rows + (dev_sparse ? 0 : sn));
+            if (rc != MMC_OK) return rc;
+            CU(ctx, cudaEventRecord(ctx->ev_d0, ctx->fin_stream));
+            CU(ctx, cudaMemcpyAsync(ctx->h_rows, src, sizeof(FreqRecDev) * n_dev_rows, cudaMemcpyDeviceToHost, ctx->fin_stream));
+            CU(ctx, cudaEventRecord(ctx->ev_d1, ctx->fin_stream));
+            ctx->tm.d2h_bytes += sizeof(FreqRecDev) * n_dev_rows;
+        }
+    }
+    n_dense = n_dev_rows;                                     // what the host merge below (few sparse records) starts from
+    // ---- sparse side buffer: sort + reduce on the host while the dense rows are on their way back ...
+    std::vector<mmc_freq_rec_t> sparse;
+    const bool fin_trace = getenv("MMC_TRACE_FINALIZE") != nullptr;
+    const auto t_s0 = std::chrono::steady_clock::now();
+    if (!raw.empty()) {
+        std::sort(raw.begin(), raw.end(), [](const SparseRec &x, const SparseRec &y) {
+            if (x.a != y.a) return x.a < y.a;                 // tid, pos, strand, code == numeric order of a
             uint32_t xi = x.b & 0xffffu, yi = y.b & 0xffffu;
             if (xi != yi) return xi < yi;
             // hap: '*' (256) first, then 0,1,...
             int32_t xh = (int32_t)(x.b >> 16) == 256 ? -1 : (int32_t)(x.b >> 16), yh = (int32_t)(y.b >> 16) == 256 ? -1 : (int32_t)(y.b >> 16);
             return xh < yh;
         });
+        sparse.reserve(raw.size());
         for (size_t i = 0; i < raw.size();) {
+            if (raw[i].a == kSpSentinel) break;              // unused slots of the warps' chunks sort last
             size_t j = i;
             uint64_t called = 0, mod = 0;
             while (j < raw.size() && raw[j].a == raw[i].a && raw[j].b == raw[i].b) { called += raw[j].w & 0xffffu; mod += raw[j].w >> 16; ++j; }
@@ -974,25 +1112,51 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             i = j;
         }
     }
-    auto less = [](const mmc_freq_rec_t &x, const mmc_freq_rec_t &y) {
-        if (x.tid != y.tid) return x.tid < y.tid;
-        if (x.pos != y.pos) return x.pos < y.pos;
-        if (x.strand != y.strand) return x.strand < y.strand;
-        if (x.code != y.code) return x.code < y.code;
-        if (x.ins_offset != y.ins_offset) return x.ins_offset < y.ins_offset;
-        return x.hap < y.hap;
-    };
-    if (sparse.empty()) {                                    // the pinned rows are the result as they are
-        ctx->freq_out.clear();
-        *recs = n_dense ? ctx->h_rows : nullptr;
-        *n_recs = n_dense;
-    } else {
-        ctx->freq_out.clear();
-        ctx->freq_out.resize(n_dense + sparse.size());
-        std::merge(ctx->h_rows, ctx->h_rows + n_dense, sparse.begin(), sparse.end(), ctx->freq_out.begin(), less);
-        *recs = ctx->freq_out.data();
-        *n_recs = ctx->freq_out.size();
+    const auto t_s1 = std::chrono::steady_clock::now();
+    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    const auto t_s2 = std::chrono::steady_clock::now();
+    {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_f0, ctx->ev_f1) == cudaSuccess) ctx->tm.finalize_ms += ms;
+        if (n_dense && cudaEventElapsedTime(&ms, ctx->ev_d0, ctx->ev_d1) == cudaSuccess) ctx->tm.d2h_ms += ms;
     }
+    // ---- ... then merged into the pinned dense rows in place, from the back: the dense rows after each sparse row
+    // move up as one block (there are few sparse rows, so this is a handful of large memmoves, no second copy)
+    const size_t ns = sparse.size();
+    if (ns) {
+        rc = ensure_rows(n_dense + ns);                      // only allocates when there were no dense rows at all
+        if (rc != MMC_OK) return rc;
+        auto less = [](const mmc_freq_rec_t &x, const mmc_freq_rec_t &y) {
+            if (x.tid != y.tid) return x.tid < y.tid;
+            if (x.pos != y.pos) return x.pos < y.pos;
+            if (x.strand != y.strand) return x.strand < y.strand;
+            if (x.code != y.code) return x.code < y.code;
+            if (x.ins_offset != y.ins_offset) return x.ins_offset < y.ins_offset;
+            return x.hap < y.hap;
+        };
+        mmc_freq_rec_t *rows = ctx->h_rows;
+        size_t end = n_dense;                                // dense rows [0, end) are still where the copy put them
+        for (size_t j = ns; j-- > 0;) {
+            const mmc_freq_rec_t &sr = sparse[j];
+            size_t hi = end, lo = 0, step = 1;               // gallop back from end: consecutive sparse rows are close
+            while (step <= hi) {
+                if (!less(sr, rows[hi - step])) { lo = hi - step + 1; break; }
+                hi -= step; step <<= 1;
+            }
+            const size_t p = (size_t)(std::upper_bound(rows + lo, rows + hi, sr, less) - rows);   // first dense row > sr
+            if (end > p) memmove(rows + p + j + 1, rows + p, (end - p) * sizeof(mmc_freq_rec_t));
+            rows[p + j] = sr;
+            end = p;
+        }
+    }
+    if (fin_trace) {
+        const auto t_s3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[mmc finalize] %llu rows from the device (%s), %llu sparse records -> %zu rows merged on the host; host sort+reduce %.2f ms, wait for device %.2f ms, merge %.2f ms\n",
+                (unsigned long long)n_dense, dev_sparse ? "dense + sparse, merged there" : "dense", sn, ns, ms(t_s0, t_s1), ms(t_s1, t_s2), ms(t_s2, t_s3));
+    }
+    *n_recs = n_dense + ns;
+    *recs = *n_recs ? ctx->h_rows : nullptr;
     return MMC_OK;
 }
 

@@ -34,7 +34,7 @@ struct FlatParams {
 
 __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t aoff = (uint32_t)kWLutSlots * 256u + warp * F.arena_bytes;
+    const uint32_t aoff = kWHeadBytes + warp * F.arena_bytes;
     const WArena A = w_arena<false>(aoff);
     const uint32_t local_words = (F.arena_bytes - kWReadBytes) / 4u;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;

@@ -114,6 +114,19 @@ __device__ __forceinline__ WArena w_arena(uint32_t aoff) {
     return A;
 }
 
+// Sparse records (mmc_device.cuh SparseRec) are taken from the global side buffer a chunk at a time: one
+// atomicAdd per kSpChunk records per warp instead of one per record (whose return the warp had to wait for:
+// 16 % of the stall samples of an --insertions run, profiles/r01d).  Slots of a chunk that stay unused are
+// closed with a sentinel the host drops.
+constexpr uint32_t kSpChunk = 64;
+constexpr unsigned long long kSpSentinel = ~0ull;
+struct WSparse { unsigned long long base; uint32_t used, pad; };          // per warp, after the LUTs
+constexpr uint32_t kWHeadBytes = (uint32_t)kWLutSlots * 256u + (uint32_t)(kWThreads / 32) * (uint32_t)sizeof(WSparse);   // LUTs | WSparse[8] | arenas
+__device__ __forceinline__ WSparse *w_sparse_state() {
+    MMC_DYN_SMEM(uint4, w_dyn);
+    return reinterpret_cast<WSparse *>(reinterpret_cast<uint8_t *>(w_dyn) + (uint32_t)kWLutSlots * 256u) + (threadIdx.x >> 5);
+}
+
 struct WarpParams {
     uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(WFixed) + 256
     uint32_t *defer_list;                    // reads left to k_decode
@@ -331,15 +344,27 @@ __device__ __noinline__ bool w_ctx_slow(const DecodeParams &P, const WState &S, 
 // a count outside the dense arrays (ins_offset > 0, exotic haplotype / code id): cold
 __device__ __noinline__ void w_add_sparse(const DecodeParams &P, uint32_t tid, uint32_t rev, int32_t ref_pos, uint32_t outc,
                                           uint32_t ins16, int32_t hap, uint32_t is_mod) {
+    WSparse *sp = w_sparse_state();
 #ifdef MMC_EMUL
-    unsigned long long slot = atomicAdd(P.sparse_n, 1ull);
+    if (sp->used >= kSpChunk) { sp->base = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk); sp->used = 0; }   // lanes run one at a time here
+    unsigned long long slot = sp->base + sp->used++;
 #else
-    // one atomic per warp: the lanes that are here together take consecutive slots
-    const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)act) - 1u;
-    unsigned long long slot = 0;
-    if (lane_id == leader) slot = atomicAdd(P.sparse_n, (unsigned long long)__popc(act));
-    slot = (((unsigned long long)__shfl_sync(act, (uint32_t)(slot >> 32), (int)leader)) << 32) | __shfl_sync(act, (uint32_t)slot, (int)leader);
-    slot += (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
+    // the lanes that are here together take consecutive slots of the warp's chunk
+    const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)act) - 1u, n = (uint32_t)__popc(act);
+    unsigned long long base = 0;
+    uint32_t used = 0;
+    if (lane_id == leader) {
+        used = sp->used; base = sp->base;
+        if (used + n > kSpChunk) {                                   // close this chunk, open the next
+            for (uint32_t u = used; u < kSpChunk; ++u)
+                if (base + u < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[base + u] = z; }
+            base = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk); used = 0;
+        }
+        sp->base = base; sp->used = used + n;
+    }
+    base = (((unsigned long long)__shfl_sync(act, (uint32_t)(base >> 32), (int)leader)) << 32) | __shfl_sync(act, (uint32_t)base, (int)leader);
+    used = __shfl_sync(act, used, (int)leader);
+    const unsigned long long slot = base + used + (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
 #endif
     if (slot < P.sparse_cap) {
         SparseRec s;
@@ -1115,13 +1140,26 @@ __device__ __noinline__ void w_fused_implicit(const DecodeParams &P, uint32_t ao
 //        header parser and the CIGAR scan out of its instruction footprint.
 struct PreParams { const WRead *reads; uint32_t n; };
 
+__device__ __forceinline__ void w_sparse_open(uint32_t lane) {
+    if (lane == 0) { WSparse *sp = w_sparse_state(); sp->base = 0; sp->used = kSpChunk; }   // nothing reserved yet
+    __syncwarp();
+}
+__device__ __forceinline__ void w_sparse_close(const DecodeParams &P, uint32_t lane) {     // the unused tail of the warp's last chunk
+    __syncwarp();
+    const WSparse *sp = w_sparse_state();
+    const unsigned long long base = sp->base;
+    for (uint32_t u = sp->used + lane; u < kSpChunk; u += 32u)
+        if (base + u < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[base + u] = z; }
+}
+
 template <int MINB, bool PRE>
 __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_constant__ DecodeParams P, const __grid_constant__ WarpParams W,
                                                                  const __grid_constant__ PreParams Q) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t aoff = (uint32_t)kWLutSlots * 256u + warp * W.arena_bytes;
+    const uint32_t aoff = kWHeadBytes + warp * W.arena_bytes;
     const WArena A = w_arena(aoff);
     w_stage_luts(P, A.s_lut);
+    w_sparse_open(lane);
     WRead *R = A.R;
     uint32_t *flex = A.flex;
     const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
@@ -1190,6 +1228,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
         }
         if (err) w_report(P, S.r, err, lane);
     }
+    w_sparse_close(P, lane);
 }
 
 }  // namespace mmc

@@ -1,0 +1,114 @@
+// mmc_sparse.cuh -- finalize of the sparse side buffer on the device (sm_100a).
+//
+// Counts that have no dense cell (ins_offset > 0 under --insertions, haplotype / code ids beyond the
+// dense slots) are appended by the decode kernels as SparseRec {a, b, w}.  With --insertions on
+// ONT reads they are a quarter of all output rows (3.8 M records per 149 k-read pass of BASELINE
+// config 3), and sorting them on the host took 240 ms of a 380 ms pass.  So the collect + sort of
+// print_freq_output() (src/mod.c:644-664) for these rows is done here:
+//
+//   k_sparse_keys     record -> 25-bit minor key (ins_offset, haplotype order) + its index
+//   [radix sort by the minor key, then a stable radix sort by the 64-bit major key a:
+//    cub::DeviceRadixSort, library code like the prefix sum below]
+//   k_sparse_gather   major key of the records in minor-key order
+//   k_sparse_heads    first record of every (a, b) run
+//   k_sparse_emit     one output row per run: n_called / n_mod summed over the run
+//   k_merge_rows      dense rows (already position ordered) and sparse rows -> one ordered array,
+//                     each row placed by a binary search in the other list (both fit in L2)
+//
+// Row order is the reference's (contig, pos, strand, code, ins_offset, haplotype with '*' first).
+#ifndef MMC_SPARSE_CUH
+#define MMC_SPARSE_CUH
+
+#include "mmc_device.cuh"
+#include "mmc_decode_warp.cuh"
+
+namespace mmc {
+
+constexpr int kSpThreads = 256;
+
+__device__ __forceinline__ uint32_t sparse_minor(uint32_t b) {             // (ins_offset, hap) in row order: '*' (256) first
+    const uint32_t h9 = b >> 16;
+    return ((b & 0xffffu) << 9) | (h9 == 256u ? 0u : h9 + 1u);
+}
+
+__global__ void __launch_bounds__(kSpThreads) k_sparse_keys(const SparseRec *raw, uint32_t n, uint32_t *minor, uint32_t *idx) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        minor[i] = sparse_minor(raw[i].b);
+        idx[i] = i;
+    }
+}
+
+__global__ void __launch_bounds__(kSpThreads) k_sparse_gather(const SparseRec *raw, const uint32_t *idx, uint32_t n, unsigned long long *major) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) major[i] = raw[idx[i]].a;
+}
+
+// flag[i] = 1 when sorted record i starts a run of equal (a, b); the chunk sentinels (sorted last) never do
+__global__ void __launch_bounds__(kSpThreads) k_sparse_heads(const SparseRec *raw, const uint32_t *idx, uint32_t n, uint32_t *flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const SparseRec r = raw[idx[i]];
+        uint32_t f = r.a != kSpSentinel;
+        if (f && i > 0) { const SparseRec p = raw[idx[i - 1u]]; f = p.a != r.a || p.b != r.b; }
+        flag[i] = f;
+    }
+}
+
+__global__ void __launch_bounds__(kSpThreads) k_sparse_emit(const SparseRec *raw, const uint32_t *idx, const uint32_t *flag, const uint32_t *off,
+                                                            uint32_t n, FreqRecDev *rows, unsigned long long *n_rows) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i == n - 1u) *n_rows = (unsigned long long)off[i] + flag[i];
+        if (!flag[i]) continue;
+        const SparseRec r = raw[idx[i]];
+        unsigned long long called = r.w & 0xffffu, mod = r.w >> 16;
+        for (uint32_t j = i + 1u; j < n && !flag[j]; ++j) {                // the rest of the run (short: one record per read)
+            const SparseRec q = raw[idx[j]];
+            if (q.a == kSpSentinel) break;
+            called += q.w & 0xffffu; mod += q.w >> 16;
+        }
+        FreqRecDev o;
+        o.tid = (int32_t)(r.a >> 41); o.pos = (int32_t)((r.a >> 9) & 0xffffffffull);
+        o.n_called = (uint32_t)called; o.n_mod = (uint32_t)mod;
+        o.ins_offset = (uint16_t)(r.b & 0xffffu);
+        const uint32_t h9 = r.b >> 16;
+        o.hap = h9 == 256u ? (int16_t)-1 : (int16_t)h9;
+        o.strand = (uint8_t)((r.a >> 8) & 1u); o.code = (uint8_t)(r.a & 0xffu); o.reserved = 0;
+        rows[off[i]] = o;
+    }
+}
+
+struct RowKey { unsigned long long hi; uint32_t lo; };
+__device__ __forceinline__ RowKey row_key(const FreqRecDev &r) {
+    RowKey k;
+    k.hi = ((unsigned long long)(uint32_t)r.tid << 41) | ((unsigned long long)(uint32_t)r.pos << 9) | ((unsigned long long)r.strand << 8) | r.code;
+    k.lo = ((uint32_t)r.ins_offset << 9) | (uint32_t)((int32_t)r.hap + 1);
+    return k;
+}
+__device__ __forceinline__ bool key_less(const RowKey &x, const RowKey &y) { return x.hi != y.hi ? x.hi < y.hi : x.lo < y.lo; }
+
+// number of rows of v[0..n) whose key is < k  (no key occurs in both lists)
+__device__ __forceinline__ unsigned long long rows_below(const FreqRecDev *v, unsigned long long n, const RowKey &k) {
+    unsigned long long lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (key_less(row_key(v[mid]), k)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kSpThreads) k_merge_rows(const FreqRecDev *dense, unsigned long long n_dense, const FreqRecDev *sparse, unsigned long long n_sparse,
+                                                           FreqRecDev *out) {
+    const unsigned long long total = n_dense + n_sparse;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (i < n_dense) {
+            const FreqRecDev r = dense[i];
+            out[i + rows_below(sparse, n_sparse, row_key(r))] = r;
+        } else {
+            const unsigned long long j = i - n_dense;
+            const FreqRecDev r = sparse[j];
+            out[j + rows_below(dense, n_dense, row_key(r))] = r;
+        }
+    }
+}
+
+}  // namespace mmc
+
+#endif  // MMC_SPARSE_CUH

@@ -45,3 +45,13 @@ def test_decode_paths_agree(emul_lib, monkeypatch, path, arena, name):
     case = [c for c in GOLDEN_CASES if c[0] == name][0]
     out = run_case(emul_lib, *case[1:])
     assert sorted_lines(out) == sorted_lines(golden_bytes(name))
+
+
+@pytest.mark.parametrize("name", ["test17a.tsv", "test5a.tsv"])
+def test_sparse_rows_sorted_on_device(emul_lib, monkeypatch, name):
+    """--insertions / haplotype rows through the device-side sort + merge of the sparse side buffer
+    (mmc_sparse.cuh; normally only taken above 65536 records) instead of the host sort."""
+    monkeypatch.setenv("MMC_SPARSE_DEVICE_MIN", "0")
+    case = [c for c in GOLDEN_CASES if c[0] == name][0]
+    out = run_case(emul_lib, *case[1:])
+    assert sorted_lines(out) == sorted_lines(golden_bytes(name))

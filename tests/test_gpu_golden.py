@@ -81,3 +81,13 @@ def test_cuda_decode_paths_agree(cuda_lib, monkeypatch, path, arena, occ):
     for name in ("test7.tsv", "test5a.tsv", "test5c.tsv", "test17a.tsv", "test16.tsv", "test2b.tsv", "test11.tsv"):
         case = [c for c in GOLDEN_CASES if c[0] == name][0]
         assert sorted_lines(run_case(cuda_lib, *case[1:])) == sorted_lines(golden_bytes(name)), name
+
+
+@pytest.mark.gpu
+def test_cuda_sparse_rows_sorted_on_device(cuda_lib, monkeypatch):
+    """Every freq golden with the sparse side buffer sorted, reduced and merged on the device (cub radix sort +
+    mmc_sparse.cuh) whatever its size; the default takes that path only above 65536 records."""
+    monkeypatch.setenv("MMC_SPARSE_DEVICE_MIN", "0")
+    for name in ("test17a.tsv", "test5a.tsv", "test5c.tsv", "test7.tsv", "test16.tsv", "test2b.tsv", "test11.tsv"):
+        case = [c for c in GOLDEN_CASES if c[0] == name][0]
+        assert sorted_lines(run_case(cuda_lib, *case[1:])) == sorted_lines(golden_bytes(name)), name

@@ -47,6 +47,15 @@ def test_synthetic_parity_cuda_paths(cuda_lib, monkeypatch, path, arena, config,
     assert n > 0
 
 
+@pytest.mark.parametrize("config,cov", [(3, 3.0), (6, 2.0)])
+def test_synthetic_parity_cuda_sparse_on_device(cuda_lib, monkeypatch, config, cov):
+    """--insertions (config 3) and haplotype (config 6) rows with the sparse side buffer sorted / reduced / merged
+    on the device (mmc_sparse.cuh) whatever its size."""
+    monkeypatch.setenv("MMC_SPARSE_DEVICE_MIN", "0")
+    n, st = run_synth(cuda_lib, config, 1500000, cov, "freq")
+    assert n > 0
+
+
 def test_counts_are_linear_in_passes(cuda_lib):
     """k passes over the same batch give exactly k times the counts of one pass (aggregation is a pure sum)."""
     s = Synth(2, contigs=(("chrS", 6000000),), coverage=8.0)

@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Per source line (in line order): executed warp instructions and stall samples from an ncu report.
-usage: ncu_lines_by_file.py report.ncu-rep [min_pct]"""
+usage: ncu_lines_by_file.py report.ncu-rep [min_pct] [kernel-name-regex]"""
 import csv, subprocess, sys
 rep = sys.argv[1]; minp = float(sys.argv[2]) if len(sys.argv) > 2 else 0.2
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + kern, stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 hdr = None; lines = {}; cur = None
 for r in rows:
