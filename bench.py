@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--coverage", type=float, default=0.0, help="override the 30x depth (debugging only)")
     ap.add_argument("--chunks", type=int, default=8, help="batches per job on the e2e path")
+    ap.add_argument("--seq-packing", type=int, default=2, choices=(2, 4), help="bits per base of SEQ in the host buffers (2: + exception list, expanded on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -202,6 +203,7 @@ def main():
         o.cap_mm_bytes = int(bases_cap * RATIO[1]) + 16 * reads_cap
         o.cap_ml_bytes = int(bases_cap * RATIO[2]) + 16 * reads_cap
         o.sparse_capacity = 1 << 26
+        o.seq_packing = args.seq_packing
         names = (C.c_char_p * 1)(*synth.names)
         lens = (C.c_uint32 * 1)(*synth.lens)
         ctx = C.c_void_p()
@@ -364,7 +366,10 @@ def main():
                        "l2": "inputs (%.2f GB per pass) exceed the 126 MB L2" % (alg_bytes / 1e9),
                        "sharding": "one chr22-shaped contig per GPU, no data-path collective",
                        "finalize_ms_once": tmf.finalize_ms, "finalize_wall_ms_once": 1e3 * fin_wall, "gen_s": gen_s,
-                       "e2e_chunks": chunks, "e2e_steps": e2e_steps},
+                       "e2e_chunks": chunks, "e2e_steps": e2e_steps,
+                       "seq_transport": "2 bits per base + exception list in the pinned host buffers, expanded to BAM's 4-bit form "
+                                        "by k_unpack_seq2 on upload (inside e2e; `value` starts from the expanded, HBM-resident batch)"
+                                        if args.seq_packing == 2 else "BAM 4-bit nibbles"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel": "decode stage = k_flat_setup + k_decode_warp<3,PRE> (dominant, ~80% of the stage) + the two "

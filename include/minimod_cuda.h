@@ -97,6 +97,10 @@ typedef struct {
     uint64_t view_capacity;      /* VIEW: records per batch; 0 -> derived from max_bytes */
     /* optional explicit pool capacities per batch (0 -> derived from max_bytes) */
     uint64_t cap_cigar_words, cap_seq_bytes, cap_mm_bytes, cap_ml_bytes;
+    int32_t  seq_packing;        /* how SEQ crosses PCIe: 0 or 4 -> BAM's 4-bit nibbles (batch->seq4);
+                                    2 -> 2 bits per base + an exception list (batch->seq2 / seq_exc), expanded
+                                    to the 4-bit form on the device.  SEQ is ~87 % of a batch's bytes. */
+    int32_t  reserved0;
 } mmc_opts_t;
 
 /* A batch in flight.  Replaces the per-read fields of db_t (src/minimod.h:125-160) that
@@ -108,6 +112,12 @@ typedef struct {
  *   seq4[seq_off[i] ..+(l_seq[i]+1)/2]        BAM 4-bit packed SEQ
  *   mm[mm_off[i] ..+mm_len[i]]                MM:Z text without the NUL  (get_mm_tag_ptr, src/mod.c:123-140)
  *   ml[ml_off[i] ..+ml_len[i]]                ML:B:C bytes; ml_len 0 if absent/not B,C (get_ml_tag, src/mod.c:142-185)
+ * With seq_packing == 2 the packer writes, instead of seq4,
+ *   seq2[seq_off[i]/2 ..+(l_seq[i]+3)/4]      4 bases per byte, first base in bits 7:6; A 0, C 1, G 2, T 3
+ *   seq_exc[0 .. seq_exc_used)                every base that is not A,C,G,T (stored as 0 in seq2) and the pad
+ *                                             nibble of an odd-length read: (nibble index into the seq4 pool,
+ *                                             i.e. 2*seq_off[i]+base) << 4 | BAM nt16 code (0 for the pad)
+ * and still advances seq_used in seq4 bytes; the device rebuilds the identical 4-bit pool.
  * Offsets are element indices into their pool (cigar: words; others: bytes); each must be a
  * multiple of MMC_ALIGN bytes, and every pool needs MMC_ALIGN bytes of slack after the last
  * slice (mmc_batch_acquire() sizes them so).  The host appends reads while
@@ -133,6 +143,10 @@ typedef struct {
     char     *mm;     uint64_t mm_cap,    mm_used;
     uint8_t  *ml;     uint64_t ml_cap,    ml_used;
     void     *priv;   /* library private */
+    uint8_t  *seq2;                                     /* seq_packing == 2 only */
+    uint64_t *seq_exc; uint64_t seq_exc_cap, seq_exc_used;
+    uint32_t  seq_packing;                              /* 4 or 2: which of seq4 / seq2 the packer fills */
+    uint32_t  reserved0;
 } mmc_batch_t;
 
 /* One output row of `freq`: the decoded key + value of core->freq_map

@@ -45,6 +45,8 @@ struct Slot {
     size_t arena_bytes = 0;
     size_t o_tid, o_pos, o_lseq, o_ncig, o_mmlen, o_mllen, o_cigoff, o_seqoff, o_mmoff, o_mloff, o_flag, o_hp;
     size_t o_cigar, o_seq, o_mm, o_ml;
+    size_t o_seq2 = 0, o_exc = 0, cap_exc = 0;   // seq_packing == 2: transport form of SEQ; o_seq is then device-only (last in the arena)
+    size_t h_arena_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // small device state: [0] err (u64), [1] view_n (u64), then u32: [4] work counter of k_decode_warp,
@@ -82,6 +84,7 @@ struct mmc_ctx {
     std::vector<Slot> slots;
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
+    int seq_packing = 4;                                             // opts.seq_packing, or MMC_SEQ_PACKING
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
@@ -198,10 +201,19 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     s.o_mmlen = take(R * 4); s.o_mllen = take(R * 4);
     s.o_cigoff = take(R * 8); s.o_seqoff = take(R * 8); s.o_mmoff = take(R * 8); s.o_mloff = take(R * 8);
     s.o_flag = take(R * 2); s.o_hp = take(R);
-    s.o_cigar = take(cap_cig + kSlack); s.o_seq = take(cap_seq + kSlack);
+    const bool two_bit = ctx->seq_packing == 2;
+    s.o_cigar = take(cap_cig + kSlack);
+    if (!two_bit) s.o_seq = take(cap_seq + kSlack);
     s.o_mm = take(cap_mm + kSlack); s.o_ml = take(cap_ml + kSlack);
+    s.h_arena_bytes = off;
+    if (two_bit) {                                  // 2 bits per base + exceptions cross PCIe; the 4-bit pool exists on the device only
+        s.cap_exc = R + cap_seq / 64 + 1024;
+        s.o_seq2 = take(cap_seq / 2 + kSlack); s.o_exc = take(8 * s.cap_exc);
+        s.h_arena_bytes = off;
+        s.o_seq = take(cap_seq + kSlack);
+    }
     s.arena_bytes = off;
-    CU(ctx, cudaMallocHost((void **)&s.h_arena, s.arena_bytes));
+    CU(ctx, cudaMallocHost((void **)&s.h_arena, s.h_arena_bytes));
     CU(ctx, cudaMalloc((void **)&s.d_arena, s.arena_bytes));
     CU(ctx, cudaMemset(s.d_arena, 0, s.arena_bytes));
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -224,7 +236,9 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     b.mm_off = (uint64_t *)(h + s.o_mmoff); b.ml_off = (uint64_t *)(h + s.o_mloff);
     b.flag = (uint16_t *)(h + s.o_flag); b.hp = h + s.o_hp;
     b.cigar = (uint32_t *)(h + s.o_cigar); b.cigar_cap = cap_cig / 4;
-    b.seq4 = h + s.o_seq; b.seq_cap = cap_seq;
+    b.seq4 = two_bit ? nullptr : h + s.o_seq; b.seq_cap = cap_seq;
+    b.seq_packing = two_bit ? 2u : 4u;
+    if (two_bit) { b.seq2 = h + s.o_seq2; b.seq_exc = (uint64_t *)(h + s.o_exc); b.seq_exc_cap = s.cap_exc; }
     b.mm = (char *)(h + s.o_mm); b.mm_cap = cap_mm;
     b.ml = h + s.o_ml; b.ml_cap = cap_ml;
     b.priv = &s;
@@ -268,8 +282,10 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
 int upload(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const size_t n = b.n_reads;
-    if (n > b.max_reads || b.cigar_used > b.cigar_cap || b.seq_used > b.seq_cap || b.mm_used > b.mm_cap || b.ml_used > b.ml_cap)
+    if (n > b.max_reads || b.cigar_used > b.cigar_cap || b.seq_used > b.seq_cap || b.mm_used > b.mm_cap || b.ml_used > b.ml_cap ||
+        b.seq_exc_used > b.seq_exc_cap)
         return fail(ctx, MMC_EINVAL, "batch exceeds its capacities");
+    const bool two_bit = ctx->seq_packing == 2;
     uint64_t bytes = 0;
     CU(ctx, cudaEventRecord(s.ev_h0, s.stream));
     auto cp = [&](size_t off, size_t len) -> cudaError_t {
@@ -281,8 +297,25 @@ int upload(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cp(s.o_mmlen, n * 4)); CU(ctx, cp(s.o_mllen, n * 4));
     CU(ctx, cp(s.o_cigoff, n * 8)); CU(ctx, cp(s.o_seqoff, n * 8)); CU(ctx, cp(s.o_mmoff, n * 8)); CU(ctx, cp(s.o_mloff, n * 8));
     CU(ctx, cp(s.o_flag, n * 2)); CU(ctx, cp(s.o_hp, n));
-    CU(ctx, cp(s.o_cigar, b.cigar_used * 4)); CU(ctx, cp(s.o_seq, b.seq_used));
+    CU(ctx, cp(s.o_cigar, b.cigar_used * 4));
     CU(ctx, cp(s.o_mm, b.mm_used)); CU(ctx, cp(s.o_ml, b.ml_used));
+    if (!two_bit) {
+        CU(ctx, cp(s.o_seq, b.seq_used));
+    } else if (b.seq_used) {                                    // transport form -> the 4-bit pool the kernels read
+        CU(ctx, cp(s.o_seq2, (b.seq_used + 1) / 2)); CU(ctx, cp(s.o_exc, 8 * b.seq_exc_used));
+        const uint64_t n8 = (b.seq_used + 15) / 16;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n8 + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        MMC_LAUNCH(k_unpack_seq2, grid, 256u, s.stream, (const uint2 *)(s.d_arena + s.o_seq2), (uint4 *)(s.d_arena + s.o_seq), (unsigned long long)n8);
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 1;
+        if (b.seq_exc_used) {
+            const unsigned g2 = (unsigned)std::min<uint64_t>((b.seq_exc_used + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            MMC_LAUNCH(k_patch_seq4, g2, 256u, s.stream, (const unsigned long long *)(s.d_arena + s.o_exc), (unsigned long long)b.seq_exc_used,
+                       (uint32_t *)(s.d_arena + s.o_seq));
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 1;
+        }
+    }
     CU(ctx, cudaEventRecord(s.ev_h1, s.stream));
     ctx->tm.h2d_bytes += bytes;
     s.uploaded = true; s.h2d_pending = true;
@@ -483,6 +516,8 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         else if (!strcmp(e, "split")) ctx->split_path = 1;
     }
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
+    ctx->seq_packing = opts->seq_packing == 2 ? 2 : 4;
+    if (const char *e = getenv("MMC_SEQ_PACKING")) { int v = atoi(e); if (v == 2 || v == 4) ctx->seq_packing = v; }   // test hook
     if (const char *e = getenv("MMC_SPARSE_DEVICE_MIN")) ctx->sparse_dev_min = strtoull(e, nullptr, 10);   // test hook: 0 = always sort sparse records on the device
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
         long v = atol(e);
@@ -763,7 +798,7 @@ int mmc_batch_acquire(mmc_ctx *ctx, mmc_batch_t **batch) {
     if (rc != MMC_OK) return rc;
     pick->acquired = true; pick->uploaded = false;
     mmc_batch_t &b = pick->pub;
-    b.n_reads = 0; b.cigar_used = b.seq_used = b.mm_used = b.ml_used = 0;
+    b.n_reads = 0; b.cigar_used = b.seq_used = b.mm_used = b.ml_used = 0; b.seq_exc_used = 0;
     *batch = &b;
     return MMC_OK;
 }

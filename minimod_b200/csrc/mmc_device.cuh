@@ -911,6 +911,42 @@ __global__ void __launch_bounds__(kMaxThreads) k_decode(DecodeParams P) {
 // ---------------------------------------------------------------------------------------
 // finalize: dense arrays -> position-ordered records
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------
+// SEQ transport (mmc_batch_t.seq2, include/minimod_cuda.h): SEQ is ~87 % of the bytes of a batch and the
+// end-to-end path is PCIe-bound, so the packer can send 2 bits per base plus a list of the bases that are
+// not A,C,G,T; these two kernels rebuild BAM's 4-bit pool in HBM, bit for bit, before the decode kernels run.
+//   k_unpack_seq2   8 bytes of seq2 (32 bases, first base in bits 7:6 of byte 0) -> 16 bytes of seq4
+//   k_patch_seq4    exception e: nibble (e >> 4) of the pool := e & 15
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t seq2_expand16(uint32_t v) {              // 2 bytes of seq2 -> 4 bytes of seq4
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;                                        // 2-bit group k -> low half of nibble k
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    const uint32_t x0 = v & 0x11111111u, x1 = (v >> 1) & 0x11111111u, n0 = x0 ^ 0x11111111u, n1 = x1 ^ 0x11111111u;
+    v = (n1 & n0) | ((n1 & x0) << 1) | ((x1 & n0) << 2) | ((x1 & x0) << 3);  // code c -> nt16 one-hot 1 << c
+    return ((v & 0x00ff00ffu) << 8) | ((v >> 8) & 0x00ff00ffu);              // first base of a byte in its high nibble, bytes in memory order
+}
+
+__global__ void __launch_bounds__(256) k_unpack_seq2(const uint2 *in, uint4 *out, unsigned long long n8) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint2 v = in[i];
+        uint4 o;
+        o.x = seq2_expand16(v.x); o.y = seq2_expand16(v.x >> 16); o.z = seq2_expand16(v.y); o.w = seq2_expand16(v.y >> 16);
+        out[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_patch_seq4(const unsigned long long *exc, unsigned long long n, uint32_t *seq4_words) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = exc[i], nib = e >> 4, byte = nib >> 1;
+        const uint32_t shift = (uint32_t)(byte & 3ull) * 8u + ((nib & 1ull) ? 0u : 4u);
+        uint32_t *w = seq4_words + (byte >> 2);
+        atomicAnd(w, ~(0xfu << shift));                                      // neighbours in the word may be patched by other threads
+        atomicOr(w, (uint32_t)(e & 15ull) << shift);
+    }
+}
+
 struct FinalizeParams {
     const unsigned long long *cells;   // first cell of the scanned range
     unsigned long long n_cells;

@@ -194,6 +194,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
     mo.subtool = subtool; mo.n_mods = (int32_t)mmods.size(); mo.mods = mmods.data();
     mo.insertions = opt.insertions; mo.haplotypes = opt.haplotypes; mo.device = opt.device;
     mo.n_slots = 3; mo.max_reads = (uint64_t)opt.batch_size; mo.max_bytes = (uint64_t)opt.batch_size_bases;
+    mo.seq_packing = 2;                          // SEQ crosses PCIe at 2 bits per base + exceptions
     mmc_ctx *ctx = nullptr;
     if (mmc_create(&ctx, &mo, (int32_t)names.size(), names.data(), bam.lens.data()) != MMC_OK) {
         ERROR("%s", mmc_strerror(nullptr)); exit(EXIT_FAILURE);

@@ -23,6 +23,57 @@ static uint8_t hp_of(const BamRecord &r) {
     return (uint8_t)v;
 }
 
+// ---- SEQ in its transport form (mmc_batch_t.seq2 / seq_exc, include/minimod_cuda.h): 2 bits per base, first base of
+// a byte in bits 7:6, A 0 C 1 G 2 T 3; every other nt16 code travels as 0 plus an exception entry, and so does the
+// pad nibble of an odd-length read, so that the device rebuilds BAM's 4-bit bytes exactly.
+namespace {
+inline bool nib_acgt(uint32_t n) { return n == 1 || n == 2 || n == 4 || n == 8; }
+struct Seq2Tables {
+    uint8_t code[256], bad[256];                  // per BAM byte (two bases): 4 bits of codes; any base without a code
+    Seq2Tables() {
+        auto c = [](uint32_t n) { return n == 2 ? 1u : n == 4 ? 2u : n == 8 ? 3u : 0u; };
+        for (uint32_t x = 0; x < 256; ++x) {
+            code[x] = (uint8_t)(c(x >> 4) << 2 | c(x & 15));
+            bad[x] = (uint8_t)(!nib_acgt(x >> 4) || !nib_acgt(x & 15));
+        }
+    }
+};
+const Seq2Tables kSeq2;
+}  // namespace
+
+// returns the number of exception entries written at seq_exc[seq_exc_used ..) (not yet committed), -1 if they do not fit
+static int64_t pack_seq2(mmc_batch_t *b, uint64_t s0, const uint8_t *seq, uint32_t L) {
+    uint8_t *dst = b->seq2 + s0 / 2;
+    const uint32_t nb = (L + 1) / 2, full = L / 2;            // BAM bytes; bytes that hold two bases
+    uint32_t bad = 0, j = 0;
+    for (; j + 1 < full; j += 2) {
+        dst[j >> 1] = (uint8_t)(kSeq2.code[seq[j]] << 4 | kSeq2.code[seq[j + 1]]);
+        bad |= kSeq2.bad[seq[j]] | kSeq2.bad[seq[j + 1]];
+    }
+    for (; j < nb; j += 2) {                                   // the last one or two bytes (one may hold the pad nibble)
+        const uint32_t x0 = seq[j], x1 = j + 1 < nb ? seq[j + 1] : 0x11u;
+        dst[j >> 1] = (uint8_t)(kSeq2.code[x0] << 4 | kSeq2.code[x1]);
+        if (j < full) bad |= kSeq2.bad[x0];
+        if (j + 1 < full) bad |= kSeq2.bad[x1];
+    }
+    uint64_t *e0 = b->seq_exc + b->seq_exc_used, *e = e0;
+    const uint64_t room = b->seq_exc_cap - b->seq_exc_used, base = s0 * 2;
+    if (bad || (L & 1u)) {
+        const uint32_t first = bad ? 0u : L - 1u;              // only the last byte can matter when every full byte was clean
+        for (uint32_t i = first; i < L; ++i) {
+            const uint32_t nib = (seq[i >> 1] >> ((~i & 1u) << 2)) & 15u;
+            if (nib_acgt(nib)) continue;
+            if ((uint64_t)(e - e0) >= room) return -1;
+            *e++ = ((base + i) << 4) | nib;
+        }
+        if (L & 1u) {
+            if ((uint64_t)(e - e0) >= room) return -1;
+            *e++ = (base + L) << 4;                            // BAM pads with 0
+        }
+    }
+    return (int64_t)(e - e0);
+}
+
 PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt, BatchMeta *meta) {
     // ---- filters, in the reference's order (src/minimod.c:260-284)
     if (rec.flag & 4) return kSkipped;                                   // BAM_FUNMAP
@@ -45,6 +96,12 @@ PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt
     if (b->n_reads >= b->max_reads || c0 + rec.n_cigar > b->cigar_cap || s0 + seq_bytes > b->seq_cap ||
         m0 + mm_len > b->mm_cap || l0 + ml_len > b->ml_cap)
         return kNoSpace;
+    const bool two_bit = b->seq_packing == 2;
+    int64_t n_exc = 0;
+    if (two_bit) {                                  // written past seq_used; committed with the other counters below
+        n_exc = pack_seq2(b, s0, rec.seq(), (uint32_t)rec.l_qseq);
+        if (n_exc < 0) return kNoSpace;
+    }
 
     const uint32_t i = b->n_reads;
     b->tid[i] = rec.tid; b->pos[i] = rec.pos; b->flag[i] = rec.flag;
@@ -53,7 +110,8 @@ PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt
     b->hp[i] = hp_of(rec);
     b->cigar_off[i] = c0; b->seq_off[i] = s0; b->mm_off[i] = m0; b->ml_off[i] = l0;
     memcpy(b->cigar + c0, rec.cigar(), 4 * (size_t)rec.n_cigar);
-    memcpy(b->seq4 + s0, rec.seq(), seq_bytes);
+    if (!two_bit) memcpy(b->seq4 + s0, rec.seq(), seq_bytes);
+    else b->seq_exc_used += (uint64_t)n_exc;
     memcpy(b->mm + m0, mm, mm_len);
     if (ml_len) memcpy(b->ml + l0, ml, ml_len);
     b->cigar_used = c0 + rec.n_cigar; b->seq_used = s0 + seq_bytes; b->mm_used = m0 + mm_len; b->ml_used = l0 + ml_len;
@@ -71,7 +129,7 @@ PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt
 }
 
 int BatchLoader::fill(mmc_batch_t *b, BatchMeta *meta, std::string *err) {
-    b->n_reads = 0; b->cigar_used = b->seq_used = b->mm_used = b->ml_used = 0;
+    b->n_reads = 0; b->cigar_used = b->seq_used = b->mm_used = b->ml_used = 0; b->seq_exc_used = 0;
     meta->stats = BatchStats(); meta->qname_off.clear(); meta->qnames.clear();
     BatchStats &st = meta->stats;
     // while (n_bam_recs < cap && processed_bytes < batch_size_bases), src/minimod.c:249

@@ -461,7 +461,35 @@ done:
 }
 
 /* process_db() + merge_db() (src/minimod.c:344-386) / output_db()'s collect (src/mod.c:569-593) for one batch */
-int oracle_process_batch(oracle_ctx *c, const mmc_batch_t *b) {
+static int oracle_process_batch4(oracle_ctx *c, const mmc_batch_t *b);
+
+/* The batch's SEQ in transport form (include/minimod_cuda.h, seq_packing == 2) back to BAM's 4-bit bytes, nibble by
+ * nibble: code c -> nt16 1 << c, then the exception entries verbatim.  Only the oracle does this on the CPU. */
+static uint8_t *seq4_from_transport(const mmc_batch_t *b) {
+    uint8_t *s4 = (uint8_t *)calloc(b->seq_used + 64, 1);
+    for (uint64_t i = 0; i < 2 * b->seq_used; i++) {                               /* nibble i of the pool */
+        const uint32_t code = (b->seq2[i >> 2] >> (6 - 2 * (i & 3))) & 3u;
+        s4[i >> 1] |= (uint8_t)((1u << code) << ((~i & 1) << 2));
+    }
+    for (uint64_t k = 0; k < b->seq_exc_used; k++) {
+        const uint64_t i = b->seq_exc[k] >> 4;
+        const uint32_t sh = (uint32_t)((~i & 1) << 2);
+        s4[i >> 1] = (uint8_t)((s4[i >> 1] & ~(0xfu << sh)) | ((uint32_t)(b->seq_exc[k] & 15u) << sh));
+    }
+    return s4;
+}
+
+int oracle_process_batch(oracle_ctx *c, const mmc_batch_t *b_in) {
+    mmc_batch_t tmp;
+    const mmc_batch_t *b = b_in;
+    uint8_t *s4 = NULL;
+    if (b_in->seq_packing == 2) { tmp = *b_in; s4 = seq4_from_transport(b_in); tmp.seq4 = s4; b = &tmp; }
+    int rc_all = oracle_process_batch4(c, b);
+    free(s4);
+    return rc_all;
+}
+
+static int oracle_process_batch4(oracle_ctx *c, const mmc_batch_t *b) {
     c->n_view = 0;
     for (uint32_t ri = 0; ri < b->n_reads; ri++) {
         vlist_t vl; memset(&vl, 0, sizeof(vl));

@@ -28,6 +28,7 @@
 #define __noinline__ __attribute__((noinline))
 
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct alignas(8) uint2 { uint32_t x, y; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
@@ -84,6 +85,7 @@ static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return emul_atomic_a
 static inline int atomicAdd(int *p, int v) { return emul_atomic_add(p, v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return emul_atomic_add(p, v); }
 static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+static inline uint32_t atomicAnd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o & v; return o; }
 static inline uint32_t atomicCAS(uint32_t *p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
 static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long c, unsigned long long v) { unsigned long long o = *p; if (o == c) *p = v; return o; }
 static inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }

@@ -24,10 +24,25 @@ def add_read(bp, tid, pos, flag, seq, cigar, mm, ml, hp=0):
     for k, w in enumerate(ops):
         b.cigar[c0 + k] = w
     nb = (len(seq) + 1) // 2
-    for k in range(nb):
-        hi = NT16.index(seq[2 * k])
-        lo = NT16.index(seq[2 * k + 1]) if 2 * k + 1 < len(seq) else 0
-        b.seq4[s0 + k] = (hi << 4) | lo
+    if b.seq_packing == 2:          # transport form (include/minimod_cuda.h): 2 bits per base + exceptions
+        code = {1: 0, 2: 1, 4: 2, 8: 3}
+        nibs = [NT16.index(ch) for ch in seq] + ([0] if len(seq) & 1 else [])
+        for k in range((len(seq) + 3) // 4):
+            v = 0
+            for j in range(4):
+                n = nibs[4 * k + j] if 4 * k + j < len(nibs) else 1
+                v |= code.get(n, 0) << (6 - 2 * j)
+            b.seq2[s0 // 2 + k] = v
+        for k, n in enumerate(nibs):
+            if n not in code:
+                assert b.seq_exc_used < b.seq_exc_cap
+                b.seq_exc[b.seq_exc_used] = ((2 * s0 + k) << 4) | n
+                b.seq_exc_used += 1
+    else:
+        for k in range(nb):
+            hi = NT16.index(seq[2 * k])
+            lo = NT16.index(seq[2 * k + 1]) if 2 * k + 1 < len(seq) else 0
+            b.seq4[s0 + k] = (hi << 4) | lo
     mmb = mm.encode()
     C.memmove(C.addressof(b.mm.contents) + m0, mmb, len(mmb))
     mlb = bytes(ml or b"")

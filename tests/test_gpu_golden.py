@@ -91,3 +91,12 @@ def test_cuda_sparse_rows_sorted_on_device(cuda_lib, monkeypatch):
     for name in ("test17a.tsv", "test5a.tsv", "test5c.tsv", "test7.tsv", "test16.tsv", "test2b.tsv", "test11.tsv"):
         case = [c for c in GOLDEN_CASES if c[0] == name][0]
         assert sorted_lines(run_case(cuda_lib, *case[1:])) == sorted_lines(golden_bytes(name)), name
+
+
+@pytest.mark.gpu
+def test_cuda_goldens_four_bit_seq(cuda_lib, monkeypatch):
+    """The Python mirror sends SEQ at 2 bits per base by default; the freq goldens once more with BAM's 4-bit nibbles."""
+    monkeypatch.setenv("MMC_SEQ_PACKING", "4")
+    for name in ("test17a.tsv", "test5a.tsv", "test5c.tsv", "test7.tsv", "test16.tsv", "test2b.tsv", "test11.tsv"):
+        case = [c for c in GOLDEN_CASES if c[0] == name][0]
+        assert sorted_lines(run_case(cuda_lib, *case[1:])) == sorted_lines(golden_bytes(name)), name

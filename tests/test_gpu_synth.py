@@ -56,6 +56,14 @@ def test_synthetic_parity_cuda_sparse_on_device(cuda_lib, monkeypatch, config, c
     assert n > 0
 
 
+@pytest.mark.parametrize("config,cov", [(2, 3.0), (3, 2.0), (6, 1.5), (4, 0.5)])
+def test_synthetic_parity_cuda_two_bit_seq(cuda_lib, monkeypatch, config, cov):
+    """The synthetic configs with SEQ crossing PCIe at 2 bits per base (the CLI's and bench.py's setting)."""
+    monkeypatch.setenv("MMC_SEQ_PACKING", "2")
+    n, st = run_synth(cuda_lib, config, 1000000, cov, "freq")
+    assert n > 0
+
+
 def test_counts_are_linear_in_passes(cuda_lib):
     """k passes over the same batch give exactly k times the counts of one pass (aggregation is a pure sum)."""
     s = Synth(2, contigs=(("chrS", 6000000),), coverage=8.0)
