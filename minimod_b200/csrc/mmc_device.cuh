@@ -999,33 +999,57 @@ struct FreqRecDev {                    // == mmc_freq_rec_t
     uint16_t reserved;
 };
 
-__global__ void k_emit_records(FinalizeParams p) {
-    __shared__ uint32_t ws[32];
+// One CTA (8 warps) per tile, one barrier per tile: every warp owns a contiguous eighth of the tile, counts its
+// non-zero cells (ballots over 64 cells per step), the warp totals are prefix-summed through shared memory, and each
+// warp then re-reads its slice (L1/L2-hot) and writes its rows in cell order.  Empty tiles -- most of a genome at
+// CpG density -- leave after one load of the tile's count.
+__global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
+    __shared__ uint32_t ws[8];
+    if (p.tile_count[blockIdx.x] == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const unsigned long long c0 = (unsigned long long)blockIdx.x * p.cells_per_tile;
     unsigned long long c1 = c0 + p.cells_per_tile;
     if (c1 > p.n_cells) c1 = p.n_cells;
+    const uint32_t per_warp = p.cells_per_tile / 8u;
+    unsigned long long w0 = c0 + (unsigned long long)warp * per_warp, w1 = w0 + per_warp;
+    if (w0 > c1) w0 = c1;
+    if (w1 > c1) w1 = c1;
+    uint32_t cnt = 0;
+    for (unsigned long long cb = w0; cb < w1; cb += 64u) {
+        const unsigned long long c = cb + lane;
+        const unsigned long long v0 = c < w1 ? p.cells[c] : 0ull, v1 = c + 32u < w1 ? p.cells[c + 32u] : 0ull;
+        cnt += (uint32_t)__popc(__ballot_sync(0xffffffffu, v0 != 0ull)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, v1 != 0ull));
+    }
+    if (lane == 0) ws[warp] = cnt;
+    __syncthreads();
+    if (cnt == 0u) return;
+    uint32_t running = 0;
+    for (uint32_t w = 0; w < warp; ++w) running += ws[w];
     FreqRecDev *out = reinterpret_cast<FreqRecDev *>(p.out) + p.out_base + p.tile_offset[blockIdx.x];
     const uint32_t spp = 2u * (uint32_t)p.n_code_slots * (uint32_t)p.n_hap_slots;   // slots per position
-    uint32_t running = 0;
-    for (unsigned long long cb = c0; cb < c1; cb += blockDim.x) {
-        unsigned long long c = cb + threadIdx.x;
-        unsigned long long v = c < c1 ? p.cells[c] : 0ull;
-        uint32_t e = v != 0ull, d = 0, tot, td;
-        block_scan2_sat(e, d, tot, td, ws);
-        if (v != 0ull) {
-            unsigned long long posi = c / spp;
-            uint32_t slot = (uint32_t)(c - posi * spp);
-            uint32_t hslot = slot % (uint32_t)p.n_hap_slots; slot /= (uint32_t)p.n_hap_slots;
-            uint32_t code = slot % (uint32_t)p.n_code_slots; slot /= (uint32_t)p.n_code_slots;
+    for (unsigned long long cb = w0; cb < w1; cb += 64u) {
+        const unsigned long long c = cb + lane;
+        const unsigned long long v0 = c < w1 ? p.cells[c] : 0ull, v1 = c + 32u < w1 ? p.cells[c + 32u] : 0ull;
+        const uint32_t f0 = __ballot_sync(0xffffffffu, v0 != 0ull), f1 = __ballot_sync(0xffffffffu, v1 != 0ull);
+        if (!(f0 | f1)) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const unsigned long long v = half ? v1 : v0, cc = half ? c + 32u : c;
+            if (v == 0ull) continue;
+            const uint32_t at = running + (half ? (uint32_t)__popc(f0) + (uint32_t)__popc(f1 & lt) : (uint32_t)__popc(f0 & lt));
+            const unsigned long long posi = cc / spp;
+            uint32_t slot = (uint32_t)(cc - posi * spp);
+            const uint32_t hslot = slot % (uint32_t)p.n_hap_slots; slot /= (uint32_t)p.n_hap_slots;
+            const uint32_t code = slot % (uint32_t)p.n_code_slots; slot /= (uint32_t)p.n_code_slots;
             FreqRecDev rec;
             rec.tid = p.tid; rec.pos = p.lo + (int32_t)posi;
             rec.n_called = (uint32_t)v; rec.n_mod = (uint32_t)(v >> 32);
             rec.ins_offset = 0;
             rec.hap = p.haplotypes ? (int16_t)((int32_t)hslot - 1) : (int16_t)-1;
             rec.strand = (uint8_t)slot; rec.code = (uint8_t)code; rec.reserved = 0;
-            out[running + e] = rec;
+            out[at] = rec;
         }
-        running += tot;
+        running += (uint32_t)__popc(f0) + (uint32_t)__popc(f1);
     }
 }
 
