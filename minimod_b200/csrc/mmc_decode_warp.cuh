@@ -120,7 +120,7 @@ __device__ __forceinline__ WArena w_arena(uint32_t aoff) {
 // closed with a sentinel the host drops.
 constexpr uint32_t kSpChunk = 64;
 constexpr unsigned long long kSpSentinel = ~0ull;
-struct WSparse { unsigned long long base; uint32_t used, pad; };          // per warp, after the LUTs
+struct WSparse { unsigned long long state, pad; };                        // per warp, after the LUTs: (first slot of the chunk << 8) | slots used
 constexpr uint32_t kWHeadBytes = (uint32_t)kWLutSlots * 256u + (uint32_t)(kWThreads / 32) * (uint32_t)sizeof(WSparse);   // LUTs | WSparse[8] | arenas
 __device__ __forceinline__ WSparse *w_sparse_state() {
     MMC_DYN_SMEM(uint4, w_dyn);
@@ -341,30 +341,46 @@ __device__ __noinline__ bool w_ctx_slow(const DecodeParams &P, const WState &S, 
     return ref_letter(cd, ref_pos) == nt16_letter(nib);
 }
 
-// a count outside the dense arrays (ins_offset > 0, exotic haplotype / code id): cold
+__device__ __forceinline__ void w_sparse_sentinel(const DecodeParams &P, unsigned long long slot) {
+    if (slot < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[slot] = z; }
+}
+
+// a count outside the dense arrays (ins_offset > 0, exotic haplotype / code id)
 __device__ __noinline__ void w_add_sparse(const DecodeParams &P, uint32_t tid, uint32_t rev, int32_t ref_pos, uint32_t outc,
                                           uint32_t ins16, int32_t hap, uint32_t is_mod) {
     WSparse *sp = w_sparse_state();
 #ifdef MMC_EMUL
-    if (sp->used >= kSpChunk) { sp->base = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk); sp->used = 0; }   // lanes run one at a time here
-    unsigned long long slot = sp->base + sp->used++;
+    unsigned long long st = sp->state;                             // lanes run one at a time here
+    if ((st & 0xffull) >= kSpChunk) st = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk) << 8;
+    const unsigned long long slot = (st >> 8) + (st & 0xffull);
+    sp->state = st + 1ull;
 #else
-    // the lanes that are here together take consecutive slots of the warp's chunk
+    // The lanes that are here together take consecutive slots of the warp's chunk.  Diverged groups of the warp may
+    // interleave (one waits for the global atomic below while another runs), so the chunk state only changes by CAS.
     const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)act) - 1u, n = (uint32_t)__popc(act);
     unsigned long long base = 0;
-    uint32_t used = 0;
+    uint32_t start = 0;
     if (lane_id == leader) {
-        used = sp->used; base = sp->base;
-        if (used + n > kSpChunk) {                                   // close this chunk, open the next
-            for (uint32_t u = used; u < kSpChunk; ++u)
-                if (base + u < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[base + u] = z; }
-            base = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk); used = 0;
+        for (;;) {
+            const unsigned long long st = atomicAdd(&sp->state, 0ull);
+            const uint32_t used = (uint32_t)(st & 0xffull);
+            if (used + n <= kSpChunk) {
+                if (atomicCAS(&sp->state, st, st + n) != st) continue;
+                base = st >> 8; start = used;
+                break;
+            }
+            const unsigned long long closed = (st & ~0xffull) | kSpChunk;
+            if (atomicCAS(&sp->state, st, closed) != st) continue;           // the unused tail of this chunk is ours to close
+            for (uint32_t u = used; u < kSpChunk; ++u) w_sparse_sentinel(P, (st >> 8) + u);
+            base = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk);      // a fresh chunk; its first n slots are this group's
+            if (atomicCAS(&sp->state, closed, (base << 8) | n) != closed)    // another group installed its chunk meanwhile:
+                for (uint32_t u = n; u < kSpChunk; ++u) w_sparse_sentinel(P, base + u);   // keep ours private and close it
+            break;
         }
-        sp->base = base; sp->used = used + n;
     }
     base = (((unsigned long long)__shfl_sync(act, (uint32_t)(base >> 32), (int)leader)) << 32) | __shfl_sync(act, (uint32_t)base, (int)leader);
-    used = __shfl_sync(act, used, (int)leader);
-    const unsigned long long slot = base + used + (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
+    start = __shfl_sync(act, start, (int)leader);
+    const unsigned long long slot = base + start + (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
 #endif
     if (slot < P.sparse_cap) {
         SparseRec s;
@@ -1141,15 +1157,13 @@ __device__ __noinline__ void w_fused_implicit(const DecodeParams &P, uint32_t ao
 struct PreParams { const WRead *reads; uint32_t n; };
 
 __device__ __forceinline__ void w_sparse_open(uint32_t lane) {
-    if (lane == 0) { WSparse *sp = w_sparse_state(); sp->base = 0; sp->used = kSpChunk; }   // nothing reserved yet
+    if (lane == 0) w_sparse_state()->state = kSpChunk;                                       // nothing reserved yet
     __syncwarp();
 }
 __device__ __forceinline__ void w_sparse_close(const DecodeParams &P, uint32_t lane) {     // the unused tail of the warp's last chunk
     __syncwarp();
-    const WSparse *sp = w_sparse_state();
-    const unsigned long long base = sp->base;
-    for (uint32_t u = sp->used + lane; u < kSpChunk; u += 32u)
-        if (base + u < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[base + u] = z; }
+    const unsigned long long st = w_sparse_state()->state;
+    for (uint32_t u = (uint32_t)(st & 0xffull) + lane; u < kSpChunk; u += 32u) w_sparse_sentinel(P, (st >> 8) + u);
 }
 
 template <int MINB, bool PRE>
