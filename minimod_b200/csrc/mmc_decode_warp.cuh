@@ -705,14 +705,19 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     }
 
     // ---- CIGAR prefix sums == get_aln() (src/mod.c:811-880)
-    uint32_t carry_q = 0, carry_r = 0;
+    // 32 ops per step; the next step's words are loaded before this step's are used.  Plain warp scans are exact while
+    // every length is < 2^26 (32 x 2^26 = 2^31; the running totals saturate at kSat like sat_add); a read with a longer
+    // op is left to k_decode, whose block scans saturate at every step.
+    uint32_t carry_q = 0, carry_r = 0, big = 0;
     const uint32_t cmask = (1u << cshift) - 1u;
+    const uint32_t rem_ref = (pos >= 0 && (uint32_t)pos < ref_len) ? ref_len - (uint32_t)pos : 0u;   // reference bases from pos on
     if (n_cig == 0u && lane == 0) { flex[o_cq] = 15u; flex[o_cr] = 0; }
+    uint32_t w_next = lane < n_cig ? ldg32(cig + lane) : 0u;
     for (uint32_t base = 0; base < n_cig; base += 32u) {
-        const uint32_t i = base + lane;
+        const uint32_t i = base + lane, w = w_next;
+        if (i + 32u < n_cig) w_next = ldg32(cig + i + 32u);
         uint32_t op = 15u, len = 0, ql = 0, rl = 0;
         if (i < n_cig) {
-            const uint32_t w = cig[i];
             op = w & 15u; len = w >> 4;
             if (op == 0u || op == 7u || op == 8u) { ql = len; rl = len; }
             else if (op == 1u || op == 4u) ql = len;
@@ -720,24 +725,27 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
             else if (op == 5u) w_raise(R, kErrHardClip);
             else w_raise(R, kErrCigarOp);
         }
-        const uint32_t iq = warp_incl_scan_sat(ql, lane), ir = warp_incl_scan_sat(rl, lane);
+        big |= len >> 26;
+        const uint32_t iq = warp_incl_scan(ql, lane), ir = warp_incl_scan(rl, lane);
         if (i < n_cig) {
-            const uint32_t q0 = sat_add(carry_q, iq >= kSat ? kSat : iq - ql), r0 = sat_add(carry_r, ir >= kSat ? kSat : ir - rl);
-            const bool alnop = op == 0u || op == 7u || op == 8u;
-            if ((alnop || (op == 1u && P.insertions)) && len > 0 && sat_add(q0, ql) > L) w_raise(R, kErrCigarLen);
-            if (alnop && len > 0) {
-                const long long last = (long long)pos + r0 + len - 1;
-                if (pos < 0 || last >= (long long)ref_len) w_raise(R, kErrRefRange);
+            uint32_t q0 = carry_q + (iq - ql), r0 = carry_r + (ir - rl);
+            if (q0 > kSat) q0 = kSat;
+            if (r0 > kSat) r0 = kSat;
+            if (len > 0u) {
+                const bool alnop = op == 0u || op == 7u || op == 8u;
+                if ((alnop || (op == 1u && P.insertions)) && q0 + ql > L) w_raise(R, kErrCigarLen);
+                if (alnop && r0 + len > rem_ref) w_raise(R, kErrRefRange);           // pos + r0 + len - 1 >= ref_len, or pos < 0
             }
             if ((i & cmask) == 0u) { flex[o_cq + (i >> cshift)] = ((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op; flex[o_cr + (i >> cshift)] = r0; }
             if (ql > 0u && q0 < L) {                              // directory: sample that holds each bucket's first base
-                const uint32_t qe = sat_add(q0, ql) < L ? q0 + ql : L;
+                const uint32_t qe = q0 + ql < L ? q0 + ql : L;
                 for (uint32_t b = (q0 + (1u << gshift) - 1u) >> gshift; (b << gshift) < qe; ++b) flex[o_dir + b] = i >> cshift;
             }
         }
-        carry_q = sat_add(carry_q, __shfl_sync(kFull, iq, 31));
-        carry_r = sat_add(carry_r, __shfl_sync(kFull, ir, 31));
+        carry_q += __shfl_sync(kFull, iq, 31); if (carry_q > kSat) carry_q = kSat;
+        carry_r += __shfl_sync(kFull, ir, 31); if (carry_r > kSat) carry_r = kSat;
     }
+    if (__ballot_sync(kFull, big != 0u)) { w_defer(defer_list, defer_n, r, lane); return false; }
     if (lane == 0) S.total_q = carry_q < L ? carry_q : L;
     uint32_t err = w_err(R);
     if (!err) err = herr;

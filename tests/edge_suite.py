@@ -156,6 +156,16 @@ def b_long_read(bp):
 
 LONG_REF = "".join(random.Random(5).choice("ACGT") for _ in range(90000))
 
+def b_huge_ops(bp):
+    """CIGAR lengths >= 2^26: the warp kernels' plain prefix scans leave such reads to k_decode (saturating scans).
+    Forward strand only: a CIGAR longer than the read on a reverse read is fatal in the reference (its reversed walk starts
+    with the clip) and a documented deviation here."""
+    seq = fwd_read(90, 100)
+    mm, cnt = mm_for(seq, "C", "m", "?")
+    add_read(bp, 0, 90, 0, seq, "100M100000000S", mm, ml_bytes(cnt))      # clip far beyond the read: not checked (src/mod.c:841-861)
+    add_read(bp, 0, 90, 0, seq, "100M", mm, ml_bytes(cnt))
+
+
 CASES = [
     case("fwd_cpg", lambda bp: build_basic(bp)),
     case("rev_cpg", lambda bp: build_basic(bp, rev=True)),
@@ -184,6 +194,7 @@ CASES = [
     case("long_read_scratch", b_long_read, contigs="long", codes="m[*]"),
     case("long_read_insertions", b_long_read, contigs="long", codes="m[C]", insertions=True),
     case("wild_dense_codes_overflow", b_lower_and_chebi, codes="*", opts=dict(dense_codes=1)),
+    case("huge_cigar_ops", b_huge_ops),
     case("no_reads", lambda bp: None),
 ]
 
@@ -210,6 +221,19 @@ def run_case(lib, c):
                 assert p.device_view() == p.oracle_view()
         finally:
             p.close()
+
+
+def f_huge_refskip(bp):
+    seq = fwd_read(90, 100)
+    mm, cnt = mm_for(seq, "C", "m", "?")
+    build_basic(bp)
+    add_read(bp, 0, 90, 0, seq, "50M100000000N50M", mm, ml_bytes(cnt))                      # lands far past the contig end
+
+
+def f_huge_leading_clip(bp):
+    seq = fwd_read(90, 100)
+    mm, cnt = mm_for(seq, "C", "m", "?")
+    add_read(bp, 0, 90, 0, seq, "70000000S100M", mm, ml_bytes(cnt))                         # the M op starts beyond the read
 
 
 def f_hardclip(bp):
@@ -272,7 +296,7 @@ def f_past_contig_end(bp):
 
 FATAL = [dict(id=f.__name__[2:], build=f) for f in
          (f_hardclip, f_bad_op, f_short_ml, f_no_ml, f_bad_base, f_bad_strand, f_empty_block, f_mixed_code, f_rank_overflow,
-          f_unknown_contig, f_past_contig_end)]
+          f_unknown_contig, f_past_contig_end, f_huge_refskip, f_huge_leading_clip)]
 
 
 def run_fatal(lib, c):
