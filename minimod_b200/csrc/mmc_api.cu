@@ -89,7 +89,7 @@ struct mmc_ctx {
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
     // [0] unused; chosen per batch from the reads' sizes unless MMC_WARP_OCC pins one.
-    uint32_t wv_arena[5] = {0, 28672u, 14192u, 9328u, 6896u};   // (228 KB / MINB - 1 KB - kWHeadBytes) / 8 warps
+    uint32_t wv_arena[5] = {0, 28672u, 14208u, 9344u, 6912u};   // (228 KB / MINB - 1 KB - kWHeadBytes) / 8 warps
     uint32_t wv_setup_arena[5] = {0, 0, 0, 0, 0};               // k_flat_setup: WRead + room for dir | cq | cr
     int wv_ctas[5] = {0, 1, 1, 1, 1};
     int w_pinned = 0;                          // MMC_WARP_OCC / MMC_WARP_ARENA given: no per-batch choice

@@ -114,18 +114,8 @@ __device__ __forceinline__ WArena w_arena(uint32_t aoff) {
     return A;
 }
 
-// Sparse records (mmc_device.cuh SparseRec) are taken from the global side buffer a chunk at a time: one
-// atomicAdd per kSpChunk records per warp instead of one per record (whose return the warp had to wait for:
-// 16 % of the stall samples of an --insertions run, profiles/r01d).  Slots of a chunk that stay unused are
-// closed with a sentinel the host drops.
-constexpr uint32_t kSpChunk = 64;
-constexpr unsigned long long kSpSentinel = ~0ull;
-struct WSparse { unsigned long long state, pad; };                        // per warp, after the LUTs: (first slot of the chunk << 8) | slots used
-constexpr uint32_t kWHeadBytes = (uint32_t)kWLutSlots * 256u + (uint32_t)(kWThreads / 32) * (uint32_t)sizeof(WSparse);   // LUTs | WSparse[8] | arenas
-__device__ __forceinline__ WSparse *w_sparse_state() {
-    MMC_DYN_SMEM(uint4, w_dyn);
-    return reinterpret_cast<WSparse *>(reinterpret_cast<uint8_t *>(w_dyn) + (uint32_t)kWLutSlots * 256u) + (threadIdx.x >> 5);
-}
+constexpr uint32_t kWHeadBytes = (uint32_t)kWLutSlots * 256u;             // call LUTs, then the warps' arenas
+constexpr unsigned long long kSpSentinel = ~0ull;                         // never a valid SparseRec.a; finalize skips it
 
 struct WarpParams {
     uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(WFixed) + 256
@@ -341,46 +331,21 @@ __device__ __noinline__ bool w_ctx_slow(const DecodeParams &P, const WState &S, 
     return ref_letter(cd, ref_pos) == nt16_letter(nib);
 }
 
-__device__ __forceinline__ void w_sparse_sentinel(const DecodeParams &P, unsigned long long slot) {
-    if (slot < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[slot] = z; }
-}
-
 // a count outside the dense arrays (ins_offset > 0, exotic haplotype / code id)
+// (A per-warp chunk reservation -- one global atomic per 64 records instead of one per group of lanes -- was 10 % faster
+// on ONT + --insertions but needs shared state that diverged groups of one warp update concurrently; the CAS version of
+// it hung on real '.'-status data, so the side buffer stays with the stateless form below.)
 __device__ __noinline__ void w_add_sparse(const DecodeParams &P, uint32_t tid, uint32_t rev, int32_t ref_pos, uint32_t outc,
                                           uint32_t ins16, int32_t hap, uint32_t is_mod) {
-    WSparse *sp = w_sparse_state();
 #ifdef MMC_EMUL
-    unsigned long long st = sp->state;                             // lanes run one at a time here
-    if ((st & 0xffull) >= kSpChunk) st = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk) << 8;
-    const unsigned long long slot = (st >> 8) + (st & 0xffull);
-    sp->state = st + 1ull;
+    unsigned long long slot = atomicAdd(P.sparse_n, 1ull);
 #else
-    // The lanes that are here together take consecutive slots of the warp's chunk.  Diverged groups of the warp may
-    // interleave (one waits for the global atomic below while another runs), so the chunk state only changes by CAS.
-    const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)act) - 1u, n = (uint32_t)__popc(act);
-    unsigned long long base = 0;
-    uint32_t start = 0;
-    if (lane_id == leader) {
-        for (;;) {
-            const unsigned long long st = atomicAdd(&sp->state, 0ull);
-            const uint32_t used = (uint32_t)(st & 0xffull);
-            if (used + n <= kSpChunk) {
-                if (atomicCAS(&sp->state, st, st + n) != st) continue;
-                base = st >> 8; start = used;
-                break;
-            }
-            const unsigned long long closed = (st & ~0xffull) | kSpChunk;
-            if (atomicCAS(&sp->state, st, closed) != st) continue;           // the unused tail of this chunk is ours to close
-            for (uint32_t u = used; u < kSpChunk; ++u) w_sparse_sentinel(P, (st >> 8) + u);
-            base = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk);      // a fresh chunk; its first n slots are this group's
-            if (atomicCAS(&sp->state, closed, (base << 8) | n) != closed)    // another group installed its chunk meanwhile:
-                for (uint32_t u = n; u < kSpChunk; ++u) w_sparse_sentinel(P, base + u);   // keep ours private and close it
-            break;
-        }
-    }
-    base = (((unsigned long long)__shfl_sync(act, (uint32_t)(base >> 32), (int)leader)) << 32) | __shfl_sync(act, (uint32_t)base, (int)leader);
-    start = __shfl_sync(act, start, (int)leader);
-    const unsigned long long slot = base + start + (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
+    // one atomic per group of lanes that are here together: they take consecutive slots
+    const uint32_t act = __activemask(), lane_id = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)act) - 1u;
+    unsigned long long slot = 0;
+    if (lane_id == leader) slot = atomicAdd(P.sparse_n, (unsigned long long)__popc(act));
+    slot = (((unsigned long long)__shfl_sync(act, (uint32_t)(slot >> 32), (int)leader)) << 32) | __shfl_sync(act, (uint32_t)slot, (int)leader);
+    slot += (unsigned long long)__popc(act & ((1u << lane_id) - 1u));
 #endif
     if (slot < P.sparse_cap) {
         SparseRec s;
@@ -1164,16 +1129,6 @@ __device__ __noinline__ void w_fused_implicit(const DecodeParams &P, uint32_t ao
 //        header parser and the CIGAR scan out of its instruction footprint.
 struct PreParams { const WRead *reads; uint32_t n; };
 
-__device__ __forceinline__ void w_sparse_open(uint32_t lane) {
-    if (lane == 0) w_sparse_state()->state = kSpChunk;                                       // nothing reserved yet
-    __syncwarp();
-}
-__device__ __forceinline__ void w_sparse_close(const DecodeParams &P, uint32_t lane) {     // the unused tail of the warp's last chunk
-    __syncwarp();
-    const unsigned long long st = w_sparse_state()->state;
-    for (uint32_t u = (uint32_t)(st & 0xffull) + lane; u < kSpChunk; u += 32u) w_sparse_sentinel(P, (st >> 8) + u);
-}
-
 template <int MINB, bool PRE>
 __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_constant__ DecodeParams P, const __grid_constant__ WarpParams W,
                                                                  const __grid_constant__ PreParams Q) {
@@ -1181,7 +1136,6 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
     const uint32_t aoff = kWHeadBytes + warp * W.arena_bytes;
     const WArena A = w_arena(aoff);
     w_stage_luts(P, A.s_lut);
-    w_sparse_open(lane);
     WRead *R = A.R;
     uint32_t *flex = A.flex;
     const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
@@ -1250,7 +1204,6 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
         }
         if (err) w_report(P, S.r, err, lane);
     }
-    w_sparse_close(P, lane);
 }
 
 }  // namespace mmc

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kSpThreads) k_sparse_gather(const SparseRec *r
 __global__ void __launch_bounds__(kSpThreads) k_sparse_heads(const SparseRec *raw, const uint32_t *idx, uint32_t n, uint32_t *flag) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const SparseRec r = raw[idx[i]];
-        uint32_t f = r.a != kSpSentinel;
+        uint32_t f = r.a != kSpSentinel;                                    // (no producer writes sentinels at present)
         if (f && i > 0) { const SparseRec p = raw[idx[i - 1u]]; f = p.a != r.a || p.b != r.b; }
         flag[i] = f;
     }
