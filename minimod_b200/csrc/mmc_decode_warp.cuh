@@ -92,6 +92,7 @@ struct WTile {                               // per warp, shared memory: one tex
     uint4    text[32 + 1];                   // chunk i at text[i] (+ one spill-over chunk)
     uint32_t em[32];                         // per chunk: terminator mask (',' or block end) of its 32 following bytes
     uint32_t rank[kWTokCap];                 // per token: byte offset in text -> base rank -> read position q
+    unsigned long long sp_state, sp_pad;     // sparse side buffer chunk of this warp: (first slot << 8) | slots used (w_sparse_flush)
 };
 
 struct WFixed {                              // fixed part of a warp's arena on the fused path
@@ -116,6 +117,7 @@ __device__ __forceinline__ WArena w_arena(uint32_t aoff) {
 
 constexpr uint32_t kWHeadBytes = (uint32_t)kWLutSlots * 256u;             // call LUTs, then the warps' arenas
 constexpr unsigned long long kSpSentinel = ~0ull;                         // never a valid SparseRec.a; finalize skips it
+constexpr uint32_t kSpChunk = 64;                                         // slots a warp reserves at a time (w_sparse_flush)
 
 struct WarpParams {
     uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(WFixed) + 256
@@ -332,9 +334,9 @@ __device__ __noinline__ bool w_ctx_slow(const DecodeParams &P, const WState &S, 
 }
 
 // a count outside the dense arrays (ins_offset > 0, exotic haplotype / code id)
-// (A per-warp chunk reservation -- one global atomic per 64 records instead of one per group of lanes -- was 10 % faster
-// on ONT + --insertions but needs shared state that diverged groups of one warp update concurrently; the CAS version of
-// it hung on real '.'-status data, so the side buffer stays with the stateless form below.)
+// (The fast call loop does not come here: it appends from a per-warp chunk at a converged point, w_sparse_flush below.
+// Letting diverged groups of a warp share that chunk state through CAS hung on real '.'-status data, so every other
+// caller keeps this stateless form.)
 __device__ __noinline__ void w_add_sparse(const DecodeParams &P, uint32_t tid, uint32_t rev, int32_t ref_pos, uint32_t outc,
                                           uint32_t ins16, int32_t hap, uint32_t is_mod) {
 #ifdef MMC_EMUL
@@ -354,6 +356,52 @@ __device__ __noinline__ void w_add_sparse(const DecodeParams &P, uint32_t tid, u
         s.w = 1u | (is_mod << 16);
         P.sparse[slot] = s;
     }
+}
+
+// The fast path's sparse appends, made at a point where the whole warp is converged (after each round of 32 calls):
+// the warp owns a chunk of kSpChunk slots of the side buffer and hands them out from shared memory, so the global
+// atomic -- and the wait for its result -- happens once per chunk instead of once per round.  All lanes call it;
+// nrec = records per pending lane (2 with a dense-less haplotype stratum).  Unused slots of a chunk are closed with
+// sentinels (here when a chunk is left, and by w_sparse_close at the end of the kernel).
+__device__ __forceinline__ void w_sparse_sentinel(const DecodeParams &P, unsigned long long slot) {
+    if (slot < P.sparse_cap) { SparseRec z; z.a = kSpSentinel; z.b = 0; z.w = 0; P.sparse[slot] = z; }
+}
+__device__ __forceinline__ void w_sparse_flush(const DecodeParams &P, WTile *T, bool pending, uint32_t nrec, uint32_t tid, uint32_t rev, uint32_t ref_pos,
+                                               uint32_t outc, uint32_t ins16, uint32_t hp, uint32_t is_mod, uint32_t lane) {
+    const uint32_t m = __ballot_sync(kFull, pending);
+    if (!m) return;
+    const uint32_t cnt = (uint32_t)__popc(m) * nrec, mine = (uint32_t)__popc(m & ((1u << lane) - 1u)) * nrec;
+    const unsigned long long st = T->sp_state;
+    unsigned long long base = st >> 8;
+    uint32_t used = (uint32_t)(st & 0xffull);
+    __syncwarp();
+    if (used + cnt > kSpChunk) {                                             // warp-uniform
+        for (uint32_t u = used + lane; u < kSpChunk; u += 32u) w_sparse_sentinel(P, base + u);
+        unsigned long long nb = 0;
+        if (lane == 0) nb = atomicAdd(P.sparse_n, (unsigned long long)kSpChunk);
+        base = (((unsigned long long)__shfl_sync(kFull, (uint32_t)(nb >> 32), 0)) << 32) | __shfl_sync(kFull, (uint32_t)nb, 0);
+        used = 0;
+    }
+    if (lane == 0) T->sp_state = (base << 8) | (used + cnt);
+    __syncwarp();
+    if (pending) {
+        const unsigned long long slot = base + used + mine;
+        SparseRec r;
+        r.a = ((unsigned long long)tid << 41) | ((unsigned long long)ref_pos << 9) | ((unsigned long long)rev << 8) | outc;
+        r.w = 1u | (is_mod << 16);
+        if (nrec == 2u) { r.b = ins16 | (hp << 16); if (slot < P.sparse_cap) P.sparse[slot] = r; }
+        r.b = ins16 | (256u << 16);
+        if (slot + nrec - 1u < P.sparse_cap) P.sparse[slot + nrec - 1u] = r;
+    }
+}
+__device__ __forceinline__ void w_sparse_open(WTile *T, uint32_t lane) {
+    if (lane == 0) T->sp_state = kSpChunk;                                   // nothing reserved yet
+    __syncwarp();
+}
+__device__ __forceinline__ void w_sparse_close(const DecodeParams &P, const WTile *T, uint32_t lane) {
+    __syncwarp();
+    const unsigned long long st = T->sp_state;
+    for (uint32_t u = (uint32_t)(st & 0xffull) + lane; u < kSpChunk; u += 32u) w_sparse_sentinel(P, (st >> 8) + u);
 }
 
 __device__ __forceinline__ void w_add_cell(const DecodeParams &P, const WState &S, int32_t ref_pos, uint32_t outc,
@@ -914,7 +962,18 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
     const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
     const uint32_t hslot = EX && P.haplotypes ? S.hp + 1u : 0u, insertions = EX ? (uint32_t)P.insertions : 0u, cshift = EX ? S.cshift : 0u;
     const uint32_t ml0 = ml_base + cidx0;
-    for (uint32_t c = lane; c < n; c += 32u) {
+    // EX: every lane runs the same number of rounds and the warp meets at the top of each, where the sparse records
+    // the previous round left (ins_offset > 0: no dense cell) are appended from the warp's chunk (w_sparse_flush).
+    const uint32_t nrec = EX && hslot ? 2u : 1u;
+    uint32_t sp_pos = 0, sp_meta = 0;                                                // ins16 | is_mod << 16
+    bool pending = false;
+    for (uint32_t c = lane; EX ? c - lane < n : c < n; c += 32u) {
+        if (EX) {
+            __syncwarp();
+            w_sparse_flush(P, T, pending, nrec, (uint32_t)S.tid, rev, sp_pos, cd.outc, sp_meta & 0xffffu, S.hp, sp_meta >> 16, lane);
+            pending = false;
+            if (c >= n) continue;
+        }
         const uint32_t rank = T->rank[c];
         if (rank >= cnt_cls) { w_raise(R, kErrMMRank); continue; }                  // src/mod.c:1116
         const uint32_t mi = ml0 + c;
@@ -987,9 +1046,12 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
             red_add_u64(cell, inc);                                                 // the '*' stratum (or the only one)
             if (EX && hslot) red_add_u64(cell + hslot, inc);                        // src/mod.c:906-928
         } else {
-            if (hslot) w_add_sparse(P, (uint32_t)S.tid, rev, (int32_t)ref_pos, cd.outc, ins16, (int32_t)S.hp, (fl >> 1) & 1u);
-            w_add_sparse(P, (uint32_t)S.tid, rev, (int32_t)ref_pos, cd.outc, ins16, -1, (fl >> 1) & 1u);
+            pending = true; sp_pos = ref_pos; sp_meta = ins16 | (((fl >> 1) & 1u) << 16);
         }
+    }
+    if (EX) {
+        __syncwarp();
+        w_sparse_flush(P, T, pending, nrec, (uint32_t)S.tid, rev, sp_pos, cd.outc, sp_meta & 0xffffu, S.hp, sp_meta >> 16, lane);
     }
 }
 
@@ -1136,6 +1198,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
     const uint32_t aoff = kWHeadBytes + warp * W.arena_bytes;
     const WArena A = w_arena(aoff);
     w_stage_luts(P, A.s_lut);
+    w_sparse_open(A.T, lane);
     WRead *R = A.R;
     uint32_t *flex = A.flex;
     const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
@@ -1204,6 +1267,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) k_decode_warp(const __grid_co
         }
         if (err) w_report(P, S.r, err, lane);
     }
+    w_sparse_close(P, w_arena(kWHeadBytes + (threadIdx.x >> 5) * W.arena_bytes).T, lane);   // (recomputed: nothing kept live across the read loop)
 }
 
 }  // namespace mmc
