@@ -19,6 +19,7 @@
 #include "mmc_device.cuh"
 #include "mmc_decode_warp.cuh"
 #include "mmc_decode_flat.cuh"
+#include "mmc_decode_stream.cuh"
 #include "mmc_sparse.cuh"
 #ifndef MMC_EMUL
 #include <cub/device/device_radix_sort.cuh>
@@ -64,6 +65,7 @@ struct Slot {
     bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false;
     uint32_t n_reads_submitted = 0;
     uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
+    int s_ctas = 8; uint32_t s_arena = 0;      // k_decode_stream: resident CTAs per SM and bytes of arena per warp for this batch
 };
 
 struct ContigHost {
@@ -85,6 +87,9 @@ struct mmc_ctx {
     std::string err;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
     int seq_packing = 4;                                             // opts.seq_packing, or MMC_SEQ_PACKING
+    int stream_path = 1;                       // k_flat_setup + k_decode_stream (default): streaming merge, constant shared memory per warp
+    uint32_t s_head = 256;                     // k_decode_stream: bytes of call LUTs in front of the arenas
+    int s_pinned_ctas = 0;                     // MMC_STREAM_CTAS: no per-batch choice
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
@@ -222,7 +227,7 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaMalloc((void **)&s.d_state, 128));
     CU(ctx, cudaMallocHost((void **)&s.h_state, 128));
     CU(ctx, cudaMalloc((void **)&s.d_defer_flat, sizeof(uint32_t) * std::max<size_t>(1, R)));
-    if (ctx->split_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
+    if (ctx->split_path || ctx->stream_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
     CU(ctx, cudaMalloc((void **)&s.d_defer, sizeof(uint32_t) * std::max<size_t>(1, R)));
     if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
     mmc_batch_t &b = s.pub;
@@ -277,6 +282,24 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
         while (mb > 1 && (ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed)) / 4u < p95) --mb;
     }
     s.max_cig = max_cig; s.max_l = max_l; s.pool_need = pool_need; s.variant = mb;
+    if (ctx->stream_path) {
+        // k_decode_stream: the arena of a warp holds SFixed + the read's dir | cq | cr.  Most resident CTAs per SM whose
+        // arena takes ~95 % of the reads with an un-sampled CIGAR (the rest get every 2nd / 4th ... op, w_setup_read).
+        uint32_t p95 = 64;
+        if (n > 0) {
+            for (uint32_t i = 0; i < n; ++i) need[i] = std::min<uint32_t>(160u, (b.l_seq[i] >> 8) + 2u) + 2u * b.n_cigar[i] + 8u;
+            const size_t k = (size_t)((uint64_t)(n - 1) * 95 / 100);
+            std::nth_element(need.begin(), need.begin() + k, need.end());
+            p95 = need[k];
+        }
+        int c = ctx->s_pinned_ctas ? ctx->s_pinned_ctas : 8;
+        auto arena_of = [&](int ctas) -> uint32_t {
+            const size_t per_cta = (size_t)(227 * 1024) / ctas - 1024;          // 1 KB per CTA is reserved by the driver
+            return (uint32_t)(((per_cta - ctx->s_head) / (kSThreads / 32)) & ~(size_t)15);
+        };
+        while (!ctx->s_pinned_ctas && c > 1 && (arena_of(c) - (uint32_t)sizeof(SFixed)) / 4u < p95) --c;
+        s.s_ctas = c; s.s_arena = arena_of(c);
+    }
 }
 
 int upload(mmc_ctx *ctx, Slot &s) {
@@ -384,7 +407,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
 
     FlatParams F;
     memset(&F, 0, sizeof(F));
-    if (ctx->split_path) {
+    if (ctx->split_path || ctx->stream_path) {
         if (pool_need > s.pool_words) {
             CU(ctx, cudaStreamSynchronize(s.stream));
             if (s.d_pool) CU(ctx, cudaFree(s.d_pool));
@@ -398,6 +421,24 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     }
 
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
+    if (ctx->stream_path) {
+        // default: k_flat_setup prepares every read (state + CIGAR arrays in HBM), k_decode_stream merges the calls
+        // against the SEQ stream; what k_flat_setup cannot prepare goes down the chain below
+        const uint32_t s_flex_words = (s.s_arena - (uint32_t)sizeof(SFixed)) / 4u;
+        const uint32_t setup_arena = kWReadBytes + std::min<uint32_t>(std::max<uint32_t>(4608u, (s_flex_words * 4u + 15u) & ~15u), 24576u);
+        F.arena_bytes = setup_arena; F.consumer_flex_words = s_flex_words; F.read_count = n; F.stream = 1;
+        const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
+        MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWHeadBytes + (size_t)setup_arena * (kFThreads / 32), s.stream, P, F);
+        CU(ctx, cudaGetLastError());
+        StreamParams SP; SP.arena_bytes = s.s_arena; SP.head_bytes = ctx->s_head;
+        PreParams Q; Q.reads = s.d_reads; Q.n = n;
+        const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + kSThreads / 32 - 1) / (kSThreads / 32), (uint64_t)ctx->sm_count * s.s_ctas));
+        const size_t ssmem = (size_t)ctx->s_head + (size_t)s.s_arena * (kSThreads / 32);
+        MMC_LAUNCH_SMEM((k_decode_stream<8>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 2;
+        P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7; P.work_counter = st32 + 12;
+    }
     if (ctx->warp_path) {
         // fast path: one warp per read; reads that do not fit a warp's shared-memory arena go to the list
         WarpParams W;
@@ -407,7 +448,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         if (wgrid == 0) wgrid = 1;
         const size_t wsmem = (size_t)kWHeadBytes + (size_t)w_arena_bytes * (kWThreads / 32);
         PreParams Q; Q.reads = nullptr; Q.n = 0;
-        if (ctx->split_path) {
+        if (ctx->split_path && !ctx->stream_path) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
             F.arena_bytes = setup_arena_bytes;
             F.consumer_flex_words = (w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
@@ -511,10 +552,13 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
     }
     if (const char *e = getenv("MMC_DECODE_PATH")) {         // "general": CTA-per-read kernel only (test hook / A-B timing)
-        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->split_path = 0; }
-        else if (!strcmp(e, "warp")) ctx->split_path = 0;
-        else if (!strcmp(e, "split")) ctx->split_path = 1;
+        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->split_path = 0; ctx->stream_path = 0; }
+        else if (!strcmp(e, "warp")) { ctx->split_path = 0; ctx->stream_path = 0; }
+        else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
+        else if (!strcmp(e, "stream")) ctx->stream_path = 1;
     }
+    if (const char *e = getenv("MMC_STREAM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->s_pinned_ctas = v; }   // tuning / test hook
+    ctx->s_head = (uint32_t)std::min<int>(opts->n_mods, kWLutSlots) * 256u;
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
     ctx->seq_packing = opts->seq_packing == 2 ? 2 : 4;
     if (const char *e = getenv("MMC_SEQ_PACKING")) { int v = atoi(e); if (v == 2 || v == 4) ctx->seq_packing = v; }   // test hook
@@ -548,7 +592,9 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     {
         size_t setup_max = 0;
         for (int mb = 1; mb <= 4; ++mb) setup_max = std::max(setup_max, (size_t)kWHeadBytes + (size_t)ctx->wv_setup_arena[mb] * (kFThreads / 32));
+        setup_max = std::max(setup_max, (size_t)kWHeadBytes + (size_t)(kWReadBytes + 24576u) * (kFThreads / 32));
         CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)setup_max));
+        CUC(cudaFuncSetAttribute((k_decode_stream<8>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #define MMC_WARP_ATTR(MB)                                                                                                        \
         do {                                                                                                                     \
             const size_t smem = (size_t)kWHeadBytes + (size_t)ctx->wv_arena[MB] * (kWThreads / 32);                         \

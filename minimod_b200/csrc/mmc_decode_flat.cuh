@@ -30,6 +30,7 @@ struct FlatParams {
     uint32_t read_count;
     uint32_t arena_bytes;                    // per warp, this kernel: WRead + room for dir | cq | cr
     uint32_t consumer_flex_words;            // flex capacity of the consumer's arena: decides the sampling shifts
+    uint32_t stream;                         // consumer is k_decode_stream: no rank index / bitmap in its arena
 };
 
 __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant__ DecodeParams P, const __grid_constant__ FlatParams F) {
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant_
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < F.read_count; r += n_warps) {
         WRead *G = &F.reads[r];
         __syncwarp();
-        bool ok = w_setup_read<false>(P, aoff, F.consumer_flex_words, local_words, F.defer_list, F.defer_n, r, lane);
+        bool ok = w_setup_read<false>(P, aoff, F.consumer_flex_words, local_words, F.defer_list, F.defer_n, r, lane, F.stream);
         __syncwarp();
         unsigned long long base = 0;
         const uint32_t take = ok ? A.R->st.n_stage : 0u;

@@ -609,7 +609,7 @@ __device__ __forceinline__ bool w_needs_bitmap(const WBlock *bd) { return bd->an
 //   local_words  capacity of THIS arena for dir|cq|cr (k_flat_setup's arenas are smaller than the consumer's)
 template <bool TILE>
 __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, uint32_t flex_words, uint32_t local_words,
-                                          uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane) {
+                                          uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane, uint32_t stream = 0u) {
     const WArena A = w_arena<TILE>(aoff);
     WRead *R = A.R;
     uint32_t *flex = A.flex;
@@ -681,7 +681,8 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     const uint32_t n_dir = (L >> gshift) + 2u;
     const uint32_t n_rd = (L >> 6) + 2u;
     const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
-    const uint32_t n_idx = idx_mask ? 1u : 0u, n_bm = bm_mask ? 1u : 0u;             // one index / bitmap, reused block after block
+    // one index / bitmap, reused block after block; the streaming consumer (mmc_decode_stream.cuh) needs neither
+    const uint32_t n_idx = (idx_mask && !stream) ? 1u : 0u, n_bm = (bm_mask && !stream) ? 1u : 0u;
     const uint32_t cap = flex_words;
     (void)cls_set;
     uint32_t cshift = 0, ishift = 0, n_samp, n_ent, need;
@@ -692,8 +693,8 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
         n_ent = (n_u4 + (1u << ishift) - 1u) >> ishift;
         need = a4(n_dir + 2u * n_samp) + n_idx * a4(n_ent + 2u + n_rd) + n_bm * a4(bm_words);   // 16-byte aligned pieces
         if (need <= cap && a4(n_dir + 2u * n_samp) <= local_words) break;
-        if (cshift >= (uint32_t)kWMaxCShift && ishift >= (uint32_t)kWMaxIShift) { w_defer(defer_list, defer_n, r, lane); return false; }
-        if ((2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
+        if (cshift >= (uint32_t)kWMaxCShift && (stream || ishift >= (uint32_t)kWMaxIShift)) { w_defer(defer_list, defer_n, r, lane); return false; }
+        if (stream || (2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
         else ++ishift;
     }
     const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = a4(o_cr + n_samp);
