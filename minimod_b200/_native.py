@@ -150,6 +150,7 @@ def _declare_host(lib):
         "mmh_write_freq": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_char_p), P(MmcFreqRec),
                                       C.c_uint64, C.c_int, P(C.c_char_p)]),
         "mmh_synth_new": (vp, [C.c_int, C.c_uint64, C.c_int, P(C.c_char_p), P(C.c_uint32), C.c_double]),
+        "mmh_synth_new2": (vp, [C.c_int, C.c_uint64, C.c_int, P(C.c_char_p), P(C.c_uint32), P(C.c_uint32), C.c_double]),
         "mmh_synth_free": (None, [vp]),
         "mmh_synth_n_reads": (C.c_uint64, [vp]),
         "mmh_synth_ref": (vp, [vp, C.c_int, P(C.c_uint64)]),

@@ -65,7 +65,7 @@ struct Slot {
     bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false;
     uint32_t n_reads_submitted = 0;
     uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
-    int s_ctas = 8; uint32_t s_arena = 0;      // k_decode_stream: resident CTAs per SM and bytes of arena per warp for this batch
+    int s_ctas = 8; uint32_t s_arena = 0, s_setup_flex = 4608;   // k_decode_stream: CTAs per SM, arena bytes per warp; k_flat_setup's room for dir | cq | cr
 };
 
 struct ContigHost {
@@ -89,7 +89,7 @@ struct mmc_ctx {
     int seq_packing = 4;                                             // opts.seq_packing, or MMC_SEQ_PACKING
     int stream_path = 1;                       // k_flat_setup + k_decode_stream (default): streaming merge, constant shared memory per warp
     uint32_t s_head = 256;                     // k_decode_stream: bytes of call LUTs in front of the arenas
-    int s_pinned_ctas = 0;                     // MMC_STREAM_CTAS: no per-batch choice
+    int s_minb = 6;                            // k_decode_stream<MINB>: resident CTAs per SM the registers are bounded for (MMC_STREAM_MINB)
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
@@ -283,8 +283,9 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
     }
     s.max_cig = max_cig; s.max_l = max_l; s.pool_need = pool_need; s.variant = mb;
     if (ctx->stream_path) {
-        // k_decode_stream: the arena of a warp holds SFixed + the read's dir | cq | cr.  Most resident CTAs per SM whose
-        // arena takes ~95 % of the reads with an un-sampled CIGAR (the rest get every 2nd / 4th ... op, w_setup_read).
+        // k_decode_stream: constant arena per warp (SFixed + room for the dir | cq | cr of short CIGARs; longer ones are
+        // looked up in the pool k_flat_setup wrote).  k_flat_setup builds the arrays in its own arena: sized for ~95 % of
+        // the reads un-sampled (the rest get every 2nd / 4th ... op, w_setup_read).
         uint32_t p95 = 64;
         if (n > 0) {
             for (uint32_t i = 0; i < n; ++i) need[i] = std::min<uint32_t>(160u, (b.l_seq[i] >> 8) + 2u) + 2u * b.n_cigar[i] + 8u;
@@ -292,13 +293,9 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
             std::nth_element(need.begin(), need.begin() + k, need.end());
             p95 = need[k];
         }
-        int c = ctx->s_pinned_ctas ? ctx->s_pinned_ctas : 8;
-        auto arena_of = [&](int ctas) -> uint32_t {
-            const size_t per_cta = (size_t)(227 * 1024) / ctas - 1024;          // 1 KB per CTA is reserved by the driver
-            return (uint32_t)(((per_cta - ctx->s_head) / (kSThreads / 32)) & ~(size_t)15);
-        };
-        while (!ctx->s_pinned_ctas && c > 1 && (arena_of(c) - (uint32_t)sizeof(SFixed)) / 4u < p95) --c;
-        s.s_ctas = c; s.s_arena = arena_of(c);
+        s.s_ctas = ctx->s_minb;
+        s.s_arena = (uint32_t)((sizeof(SFixed) + 1024 + 15) & ~(size_t)15);
+        s.s_setup_flex = std::min<uint32_t>(std::max<uint32_t>(4608u, (p95 * 4u + 15u) & ~15u), 24576u);
     }
 }
 
@@ -424,9 +421,8 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     if (ctx->stream_path) {
         // default: k_flat_setup prepares every read (state + CIGAR arrays in HBM), k_decode_stream merges the calls
         // against the SEQ stream; what k_flat_setup cannot prepare goes down the chain below
-        const uint32_t s_flex_words = (s.s_arena - (uint32_t)sizeof(SFixed)) / 4u;
-        const uint32_t setup_arena = kWReadBytes + std::min<uint32_t>(std::max<uint32_t>(4608u, (s_flex_words * 4u + 15u) & ~15u), 24576u);
-        F.arena_bytes = setup_arena; F.consumer_flex_words = s_flex_words; F.read_count = n; F.stream = 1;
+        const uint32_t setup_arena = kWReadBytes + s.s_setup_flex;
+        F.arena_bytes = setup_arena; F.consumer_flex_words = 1u << 24; F.read_count = n; F.stream = 1;
         const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
         MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWHeadBytes + (size_t)setup_arena * (kFThreads / 32), s.stream, P, F);
         CU(ctx, cudaGetLastError());
@@ -434,7 +430,10 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         PreParams Q; Q.reads = s.d_reads; Q.n = n;
         const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + kSThreads / 32 - 1) / (kSThreads / 32), (uint64_t)ctx->sm_count * s.s_ctas));
         const size_t ssmem = (size_t)ctx->s_head + (size_t)s.s_arena * (kSThreads / 32);
-        MMC_LAUNCH_SMEM((k_decode_stream<8>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
+        if (s.s_ctas == 8) MMC_LAUNCH_SMEM((k_decode_stream<8>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
+        else if (s.s_ctas == 6) MMC_LAUNCH_SMEM((k_decode_stream<6>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
+        else if (s.s_ctas == 5) MMC_LAUNCH_SMEM((k_decode_stream<5>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
+        else MMC_LAUNCH_SMEM((k_decode_stream<4>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
         CU(ctx, cudaGetLastError());
         ctx->tm.kernel_launches += 2;
         P.read_list = s.d_defer_flat; P.read_list_n = st32 + 7; P.work_counter = st32 + 12;
@@ -557,7 +556,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
         else if (!strcmp(e, "stream")) ctx->stream_path = 1;
     }
-    if (const char *e = getenv("MMC_STREAM_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->s_pinned_ctas = v; }   // tuning / test hook
+    if (const char *e = getenv("MMC_STREAM_MINB")) { int v = atoi(e); if (v == 8 || v == 6 || v == 5 || v == 4) ctx->s_minb = v; }   // tuning
     ctx->s_head = (uint32_t)std::min<int>(opts->n_mods, kWLutSlots) * 256u;
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
     ctx->seq_packing = opts->seq_packing == 2 ? 2 : 4;
@@ -594,7 +593,10 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         for (int mb = 1; mb <= 4; ++mb) setup_max = std::max(setup_max, (size_t)kWHeadBytes + (size_t)ctx->wv_setup_arena[mb] * (kFThreads / 32));
         setup_max = std::max(setup_max, (size_t)kWHeadBytes + (size_t)(kWReadBytes + 24576u) * (kFThreads / 32));
         CUC(cudaFuncSetAttribute(k_flat_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)setup_max));
-        CUC(cudaFuncSetAttribute((k_decode_stream<8>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUC(cudaFuncSetAttribute((k_decode_stream<8>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUC(cudaFuncSetAttribute((k_decode_stream<6>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUC(cudaFuncSetAttribute((k_decode_stream<5>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUC(cudaFuncSetAttribute((k_decode_stream<4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 #define MMC_WARP_ATTR(MB)                                                                                                        \
         do {                                                                                                                     \
             const size_t smem = (size_t)kWHeadBytes + (size_t)ctx->wv_arena[MB] * (kWThreads / 32);                         \

@@ -35,24 +35,6 @@ struct SRing {
     uint32_t pre[kSRing];                    // class bases of the read before that vector, in stream order
     uint32_t exp[kSRing];                    // '.' blocks: bit t <-> base t of the vector is an explicit call
 };
-struct SFixed { WRead rd; WTile tl; SRing rg; };
-struct SArena { uint8_t *s_lut; WRead *R; WTile *T; SRing *G; uint32_t *flex; };
-__device__ __forceinline__ SArena s_arena(uint32_t aoff) {
-    MMC_DYN_SMEM(uint4, w_dyn);
-    uint8_t *base = reinterpret_cast<uint8_t *>(w_dyn);
-    SArena A;
-    A.s_lut = base;
-    SFixed *sf = reinterpret_cast<SFixed *>(base + aoff);
-    A.R = &sf->rd; A.T = &sf->tl; A.G = &sf->rg;
-    A.flex = reinterpret_cast<uint32_t *>(base + aoff + (uint32_t)sizeof(SFixed));
-    return A;
-}
-
-struct StreamParams {
-    uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(SFixed) + 256
-    uint32_t head_bytes;                     // call LUTs in front of the arenas
-};
-
 // warp-uniform state of the SEQ stream of one MM block
 struct SStream {
     uint32_t p_hi;                           // vectors appended so far (stream positions [0, p_hi))
@@ -61,6 +43,25 @@ struct SStream {
     uint32_t p_ret;                          // '.' blocks: vectors before it have emitted their implicit calls
     uint32_t mode, pat;                      // 0: nibble == pat, 1: class A (everything but C,G,T,N), 2: every base (canonical base N)
     uint32_t n_u4, tail_n, rev, dot;
+};
+
+struct SFixed { WRead rd; WTile tl; SRing rg; SStream zs; uint32_t pad[2]; };
+static_assert(sizeof(SFixed) % 16 == 0, "arena pieces are 16-byte aligned");
+struct SArena { uint8_t *s_lut; WRead *R; WTile *T; SRing *G; SStream *Z; uint32_t *flex; };
+__device__ __forceinline__ SArena s_arena(uint32_t aoff) {
+    MMC_DYN_SMEM(uint4, w_dyn);
+    uint8_t *base = reinterpret_cast<uint8_t *>(w_dyn);
+    SArena A;
+    A.s_lut = base;
+    SFixed *sf = reinterpret_cast<SFixed *>(base + aoff);
+    A.R = &sf->rd; A.T = &sf->tl; A.G = &sf->rg; A.Z = &sf->zs;
+    A.flex = reinterpret_cast<uint32_t *>(base + aoff + (uint32_t)sizeof(SFixed));
+    return A;
+}
+
+struct StreamParams {
+    uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(SFixed) + 256
+    uint32_t head_bytes;                     // call LUTs in front of the arenas
 };
 
 __device__ __forceinline__ uint32_t s_flags(uint32_t u, uint32_t mode, uint32_t pat) {
@@ -115,7 +116,7 @@ __device__ __noinline__ void s_retire(const DecodeParams &P, uint32_t aoff, uint
             const uint32_t before = (uint32_t)__popc(m32 & ((1u << t) - 1u));
             const uint32_t s = pre + (rev ? tot - 1u - before : before);
             if (s >= bound) continue;
-            w_call(P, R, A.flex, A.s_lut, bd, jb, u * 32u + t, true, s, 0u, rd_code);
+            w_call(P, R, S.flex, A.s_lut, bd, jb, u * 32u + t, true, s, 0u, rd_code);
         }
     }
     __syncwarp();
@@ -159,30 +160,85 @@ __device__ __forceinline__ void s_append(const DecodeParams &P, uint32_t aoff, u
     __syncwarp();
 }
 
-// TAIL: what happens once a call's read position q is known
-//   0  fast: `freq`, one requested code (K == 1), class C/G/T, dense cell              (w_fast_ok)
-//   1  fast, class A (the read base has to be looked at for the reference comparison)
-//   2  fast + any of --insertions / --haplotypes / sampled CIGAR
-//   3  1 + 2
-//   4  general: several codes per block, `view`, canonical base N, slow contexts, ...  (w_call)
-// Returns the number of tokens (calls) of the block; per-read errors are raised in R->st.err.
-template <int TAIL>
-__device__ __forceinline__ uint32_t s_block(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t ml_base, uint32_t lane) {
-    constexpr bool FAST = TAIL < 4, C0 = TAIL == 1 || TAIL == 3, EX = TAIL == 2 || TAIL == 3;
+// ---------------------------------------------------------------------------------------
+// phase A of a text tile: base ranks T->rank[0..n) -> read positions (bases_pos[][], src/mod.c:1102-1113), in place.
+// Rounds of up to 32 calls: the stream is advanced until the round's first call is covered (and, ring permitting, its
+// last), every covered call finds its vector by binary search of the ring and selects inside the staged copy.
+// A class-A read base that is not literally 'A' is marked in bit 31 (it can never equal the reference, src/mod.c:1164).
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t n, uint32_t lane) {
     const SArena A = s_arena(aoff);
     WRead *R = A.R;
     WTile *T = A.T;
     SRing *G = A.G;
-    uint32_t *flex = A.flex;
-    WState &S = R->st;
-    const WBlock *bd = &R->blk[jb];
-    const uint32_t a0 = bd->hdr_end, a1 = bd->end;
-    const bool do_calls = bd->any_req != 0u;
-    SStream Z;
-    s_stream_open(Z, S, bd);
-    const uint8_t *seq = S.seq;
+    const uint8_t *seq = R->st.seq;
+    SStream Z = *A.Z;
+    uint32_t c0 = 0;
+    while (c0 < n) {
+        const uint32_t c = c0 + lane;
+        const uint32_t k = c < n ? T->rank[c] : 0xffffffffu;       // base rank == stream rank (src/mod.c:1098,1109-1113)
+        const uint32_t k0 = __shfl_sync(kFull, k, 0);
+        while (Z.cum <= k0 && Z.p_hi < Z.n_u4) { const uint32_t at = Z.p_hi; s_append(P, aoff, jb, seq, G, Z, lane); Z.p_cov = at; }
+        if (Z.cum <= k0) {                                         // src/mod.c:1116: more skips than bases of the class
+            w_raise(R, kErrMMRank);
+            for (uint32_t x = c; x < n; x += 32u) T->rank[x] = kNoCall;
+            break;
+        }
+        const uint32_t klast = __shfl_sync(kFull, k, (int)(n - c0 < 32u ? n - c0 - 1u : 31u));
+        while (Z.cum <= klast && Z.p_hi < Z.n_u4 && Z.p_hi + 32u <= Z.p_cov + kSRing) s_append(P, aoff, jb, seq, G, Z, lane);
+        const bool act = k < Z.cum;
+        const uint32_t am = __ballot_sync(kFull, act);
+        c0 += (uint32_t)__popc(am);
+        uint32_t p = Z.p_cov;
+        if (act) {                                                 // largest p in [p_cov, p_hi) with pre[p] <= k
+#pragma unroll
+            for (uint32_t st = kSRing / 2u; st; st >>= 1) {
+                const uint32_t t = p + st;
+                if (t < Z.p_hi && G->pre[t & kSMask] <= k) p = t;
+            }
+        }
+        Z.p_cov = __shfl_sync(kFull, p, 31 - __clz((int)am));      // the next round's first call lies at or after this vector
+        if (!act) continue;
+        const uint32_t sl = p & kSMask, u = Z.rev ? Z.n_u4 - 1u - p : p;
+        const uint4 v = G->vec[sl];
+        uint32_t rem = k - G->pre[sl];
+        const SVecFlags F = s_vec_flags(v, Z.mode, Z.pat, u == Z.n_u4 - 1u ? Z.tail_n : 32u);
+        const uint32_t s0 = (uint32_t)__popc(F.f0), s1 = s0 + (uint32_t)__popc(F.f1), s2 = s1 + (uint32_t)__popc(F.f2);
+        if (Z.rev) rem = s2 + (uint32_t)__popc(F.f3) - 1u - rem;
+        uint32_t f = F.f0, wsel = 0, sub = 0, wv = v.x;
+        if (rem >= s0) { f = F.f1; wsel = 8; sub = s0; wv = v.y; }
+        if (rem >= s1) { f = F.f2; wsel = 16; sub = s1; wv = v.z; }
+        if (rem >= s2) { f = F.f3; wsel = 24; sub = s2; wv = v.w; }
+        rem -= sub;
+        uint32_t cc = (uint32_t)__popc(f & 0xffffu);
+        if (rem >= cc) { rem -= cc; f >>= 16; wsel += 4; }
+        cc = (uint32_t)__popc(f & 0xffu);
+        if (rem >= cc) { rem -= cc; f >>= 8; wsel += 2; }
+        const uint32_t off = wsel + ((rem != 0u || !(f & 0x80u)) ? 1u : 0u);
+        uint32_t q = u * 32u + off;
+        if (Z.dot) atomicOr(&G->exp[sl], 1u << off);
+        if (Z.mode == 1u) {
+            const uint32_t o8 = off & 7u, nib = (wv >> (8u * (o8 >> 1) + ((o8 & 1u) ? 0u : 4u))) & 0xfu;
+            if (nib != 1u) q |= 0x80000000u;
+        }
+        T->rank[c] = q;
+    }
+    __syncwarp();
+    if (lane == 0) *A.Z = Z;
+    __syncwarp();
+}
 
-    // ---- per-block constants of the fast tail (same arithmetic as w_tile_calls_fast)
+// ---------------------------------------------------------------------------------------
+// phase B of a text tile, common case: read positions T->rank[0..n) -> reference positions -> context -> threshold ->
+// dense cells.  `freq`, one requested code per block (K == 1), canonical base A/C/G/T (w_fast_ok).
+//   C0  class A (bit 31 of the position: the read base is not literally 'A')
+//   EX  any of: --insertions, --haplotypes, sampled CIGAR (kept out of the lean instantiation)
+// ---------------------------------------------------------------------------------------
+template <bool C0, bool EX>
+__device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, const WBlock *bd,
+                                            uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
+    const WState &S = R->st;
+    const uint32_t *flex = S.flex;                                 // dir | cq | cr: the arena's copy, or (long CIGARs) the pool in HBM through L1
     const uint32_t *dir = flex + S.o_dir, *cq = flex + S.o_cq, *cr = flex + S.o_cr;
     const uint32_t rev = S.rev, total_q = S.total_q, g = S.gshift, last_samp = S.n_samp - 1u, ml_len = S.ml_len, ref_len = S.ref_len;
     const int32_t pos = S.pos;
@@ -193,160 +249,131 @@ __device__ __forceinline__ uint32_t s_block(const DecodeParams &P, uint32_t aoff
     const uint32_t cls = bd->cls;
     const uint32_t m = cd.ctx_mode == kCtxFast ? cd.ctx_len : 0u, pat2 = cd.pat2;
     const uint32_t m2 = (1u << (2u * m)) - 1u, m1 = (1u << m) - 1u;
-    const uint8_t *lut = A.s_lut + (cd.ri < 0 ? 0 : cd.ri) * 256;
+    // occurrences of the context that can cover the call: the one starting j bases into the window puts pattern base
+    // m-1-j on the call's position, and ref == read base (src/mod.c:1164) forces that base to be the block's class
+    uint32_t jmask = 0;
+    for (uint32_t j = 0; j < m; ++j) jmask |= (uint32_t)(((pat2 >> (2u * (m - 1u - j))) & 3u) == (C0 ? 0u : cls)) << j;
+    const uint8_t *lut = s_lut + cd.ri * 256;
     const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
     const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
     const uint32_t hslot = EX && P.haplotypes ? S.hp + 1u : 0u, insertions = EX ? (uint32_t)P.insertions : 0u, cshift = EX ? S.cshift : 0u;
     const uint32_t nrec = EX && hslot ? 2u : 1u;
-    const uint32_t rd_code = (!bd->is_n && cls >= 1u && cls <= 3u) ? cls : 4u;
+    const uint32_t ml0 = ml_base + cidx0;
     uint32_t sp_pos = 0, sp_meta = 0;                              // EX: a sparse record waiting for the next converged point
     bool pending = false;
-
-    if (lane == 0) S.carry_sum = 0;
-    __syncwarp();
-    uint32_t carry_cnt = 0;
-    bool dead = false;                                             // warp-uniform: the read is in error, stop working on the block
-    for (uint32_t tb = a0 & ~15u; tb < a1 && !dead; tb += (uint32_t)kWChunks * 16u) {
-        uint32_t sum = 0;
-        const uint32_t n = w_tile_ranks(R, T, tb, a0, a1, S.carry_sum, &sum, lane);
-        if (do_calls && n) {
-            const uint32_t ml0 = ml_base + carry_cnt;
-            uint32_t c0 = 0;
-            while (c0 < n) {
-                if (EX) {
-                    __syncwarp();
-                    w_sparse_flush(P, T, pending, nrec, (uint32_t)S.tid, rev, sp_pos, cd.outc, sp_meta & 0xffffu, S.hp, sp_meta >> 16, lane);
-                    pending = false;
+    for (uint32_t c = lane; EX ? c - lane < n : c < n; c += 32u) {
+        if (EX) {
+            __syncwarp();
+            w_sparse_flush(P, T, pending, nrec, (uint32_t)S.tid, rev, sp_pos, cd.outc, sp_meta & 0xffffu, S.hp, sp_meta >> 16, lane);
+            pending = false;
+            if (c >= n) continue;
+        }
+        const uint32_t qq = T->rank[c];
+        if (qq == kNoCall) continue;
+        const uint32_t q = qq & 0x7fffffffu;
+        const uint32_t mi = ml0 + c;
+        const uint32_t prob = mi < ml_len ? ldg8(ml + mi) : 0x100u;                    // issued early
+        // ---- map: aln[q] (get_aln, src/mod.c:776-881)
+        uint32_t ref_pos, ins16 = 0;
+        if (EX && cshift != 0u) {                                                       // sampled CIGAR (long reads): generic lookup
+            const AlnHit h = w_cigar_lookup(S, flex, q);
+            if (h.aln >= 0) ref_pos = (uint32_t)h.aln;
+            else if (insertions && h.ins >= 0) { ref_pos = (uint32_t)h.ins; ins16 = h.insoff & 0xffffu; }
+            else continue;
+        } else {
+            if (q >= total_q) continue;
+            const uint32_t b = q >> g;
+            uint32_t lo = dir[b], hi = (((b + 1u) << g) < total_q) ? dir[b + 1u] : last_samp;
+            const uint32_t qlim = (q + 1u) << 4;
+            while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (cq[mid] < qlim) lo = mid; else hi = mid - 1u; }
+            const uint32_t ce = cq[lo], op = ce & 15u;
+            if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
+            else if (EX && insertions && op == 1u) {                                    // ins[] / ins_offset (src/mod.c:1122-1127)
+                const int32_t left = pos + (int32_t)cr[lo] - 1;
+                if (left < 0) continue;                                                 // Q11
+                ref_pos = (uint32_t)left; ins16 = (q - (ce >> 4) + 1u) & 0xffffu;       // make_key's uint16_t (src/mod.c:428)
+            } else continue;                                                            // src/mod.c:1127
+        }
+        // ---- context + base test (src/mod.c:1162-1172)
+        if (m) {
+            if (ref_pos + 1u < m || ref_pos + m > ref_len) {                            // contig edge: generic test
+                if (!w_ctx_slow(P, S, (uint32_t)cd.ri, ref_pos, q, 0u)) continue;
+            } else {
+                const uint32_t w0 = ref_pos + 1u - m, wi = w0 >> 4, ei = w0 >> 5;
+                const uint32_t W = __funnelshift_r(ldg32(ref2 + wi), ldg32(ref2 + wi + 1u), (w0 & 15u) * 2u);
+                const uint32_t E = __funnelshift_r(ldg32(excm + ei), ldg32(excm + ei + 1u), w0 & 31u);
+                uint32_t hit = 0;
+                for (uint32_t jm = jmask; jm; jm &= jm - 1u) {
+                    const uint32_t j = (uint32_t)__ffs((int)jm) - 1u;
+                    hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
                 }
-                const uint32_t c = c0 + lane;
-                const uint32_t k = c < n ? T->rank[c] : 0xffffffffu;   // base rank == stream rank (src/mod.c:1098,1109-1113)
-                const uint32_t k0 = __shfl_sync(kFull, k, 0);
-                while (Z.cum <= k0 && Z.p_hi < Z.n_u4) { const uint32_t at = Z.p_hi; s_append(P, aoff, jb, seq, G, Z, lane); Z.p_cov = at; }
-                if (Z.cum <= k0) { w_raise(R, kErrMMRank); dead = true; break; }      // src/mod.c:1116
-                const uint32_t klast = __shfl_sync(kFull, k, (int)(n - c0 < 32u ? n - c0 - 1u : 31u));
-                while (Z.cum <= klast && Z.p_hi < Z.n_u4 && Z.p_hi + 32u <= Z.p_cov + kSRing) s_append(P, aoff, jb, seq, G, Z, lane);
-                const bool act = k < Z.cum;
-                const uint32_t am = __ballot_sync(kFull, act);
-                c0 += (uint32_t)__popc(am);
-                uint32_t p = Z.p_cov, prob = 0;
-                if (act) {
-                    // ---- ML byte, issued early
-                    if (FAST) { const uint32_t mi = ml0 + c; prob = mi < ml_len ? ldg8(ml + mi) : 0x100u; }
-                    // ---- the vector that holds rank k: largest p in [p_cov, p_hi) with pre[p] <= k
-#pragma unroll
-                    for (uint32_t st = kSRing / 2u; st; st >>= 1) {
-                        const uint32_t t = p + st;
-                        if (t < Z.p_hi && G->pre[t & kSMask] <= k) p = t;
-                    }
-                }
-                // the next round's first call lies at or after the last active call's vector
-                Z.p_cov = __shfl_sync(kFull, p, 31 - __clz((int)am));
-                if (!act) continue;
-                // ---- select inside the vector (bases_pos[][], src/mod.c:1102-1113)
-                const uint32_t sl = p & kSMask, u = Z.rev ? Z.n_u4 - 1u - p : p;
-                const uint4 v = G->vec[sl];
-                uint32_t rem = k - G->pre[sl];
-                const SVecFlags F = s_vec_flags(v, Z.mode, Z.pat, u == Z.n_u4 - 1u ? Z.tail_n : 32u);
-                const uint32_t s0 = (uint32_t)__popc(F.f0), s1 = s0 + (uint32_t)__popc(F.f1), s2 = s1 + (uint32_t)__popc(F.f2);
-                if (Z.rev) rem = s2 + (uint32_t)__popc(F.f3) - 1u - rem;
-                uint32_t f = F.f0, wsel = 0, sub = 0;
-                if (rem >= s0) { f = F.f1; wsel = 8; sub = s0; }
-                if (rem >= s1) { f = F.f2; wsel = 16; sub = s1; }
-                if (rem >= s2) { f = F.f3; wsel = 24; sub = s2; }
-                rem -= sub;
-                uint32_t cc = (uint32_t)__popc(f & 0xffffu);
-                if (rem >= cc) { rem -= cc; f >>= 16; wsel += 4; }
-                cc = (uint32_t)__popc(f & 0xffu);
-                if (rem >= cc) { rem -= cc; f >>= 8; wsel += 2; }
-                const uint32_t off = wsel + ((rem != 0u || !(f & 0x80u)) ? 1u : 0u);
-                const uint32_t q = u * 32u + off;
-                if (Z.dot) atomicOr(&G->exp[sl], 1u << off);
-                if (!FAST) {
-                    w_call(P, R, flex, A.s_lut, bd, jb, q, false, carry_cnt + c, ml_base, rd_code);
-                    continue;
-                }
-                // ---- map: aln[q] (get_aln, src/mod.c:776-881)
-                uint32_t ref_pos, ins16 = 0;
-                if (EX && cshift != 0u) {                                                   // sampled CIGAR (long reads): generic lookup
-                    const AlnHit h = w_cigar_lookup(S, flex, q);
-                    if (h.aln >= 0) ref_pos = (uint32_t)h.aln;
-                    else if (insertions && h.ins >= 0) { ref_pos = (uint32_t)h.ins; ins16 = h.insoff & 0xffffu; }
-                    else continue;
-                } else {
-                    if (q >= total_q) continue;
-                    const uint32_t b = q >> g;
-                    uint32_t lo = dir[b], hi = (((b + 1u) << g) < total_q) ? dir[b + 1u] : last_samp;
-                    const uint32_t qlim = (q + 1u) << 4;
-                    while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (cq[mid] < qlim) lo = mid; else hi = mid - 1u; }
-                    const uint32_t ce = cq[lo], op = ce & 15u;
-                    if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
-                    else if (EX && insertions && op == 1u) {                                // ins[] / ins_offset (src/mod.c:1122-1127)
-                        const int32_t left = pos + (int32_t)cr[lo] - 1;
-                        if (left < 0) continue;                                             // Q11
-                        ref_pos = (uint32_t)left; ins16 = (q - (ce >> 4) + 1u) & 0xffffu;   // make_key's uint16_t (src/mod.c:428)
-                    } else continue;                                                        // src/mod.c:1127
-                }
-                // ---- context + base test (src/mod.c:1162-1172)
-                if (m) {
-                    if (ref_pos + 1u < m || ref_pos + m > ref_len) {                        // contig edge: generic test
-                        if (!w_ctx_slow(P, S, (uint32_t)cd.ri, ref_pos, q, 0u)) continue;
-                    } else {
-                        const uint32_t w0 = ref_pos + 1u - m, wi = w0 >> 4, ei = w0 >> 5;
-                        const uint32_t W = __funnelshift_r(ldg32(ref2 + wi), ldg32(ref2 + wi + 1u), (w0 & 15u) * 2u);
-                        const uint32_t E = __funnelshift_r(ldg32(excm + ei), ldg32(excm + ei + 1u), w0 & 31u);
-                        uint32_t hit = 0;
-                        for (uint32_t j = 0; j < m; ++j) hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
-                        if (!hit) continue;
-                        uint32_t rc = cls;                                                  // the read base, as a 2-bit code
-                        if (C0) {                                                           // class 0 = 'A' and every other nt16 letter
-                            const uint32_t wi4 = off >> 3, wv = wi4 == 0u ? v.x : wi4 == 1u ? v.y : wi4 == 2u ? v.z : v.w;
-                            const uint32_t o8 = off & 7u, nib = (wv >> (8u * (o8 >> 1) + ((o8 & 1u) ? 0u : 4u))) & 0xfu;
-                            rc = nib == 1u ? 0u : 5u;
-                        }
-                        if (((W >> (2u * (m - 1u))) & 3u) != rc) continue;
-                    }
-                }
-                if (prob > 0xffu) { w_raise(R, kErrMLIndex); continue; }                    // src/mod.c:1174
-                const uint32_t fl = lut[prob];                                              // src/mod.c:1181-1191
-                if (!(fl & 1u)) continue;
-                const unsigned long long inc = 1ull | ((unsigned long long)((fl >> 1) & 1u) << 32);
-                if (!EX || ins16 == 0u) {
-                    unsigned long long *cell = cells + ((unsigned long long)ref_pos * per_pos + within);
-                    red_add_u64(cell, inc);                                                 // the '*' stratum (or the only one)
-                    if (EX && hslot) red_add_u64(cell + hslot, inc);                        // src/mod.c:906-928
-                } else {
-                    pending = true; sp_pos = ref_pos; sp_meta = ins16 | (((fl >> 1) & 1u) << 16);
-                }
+                if (!hit) continue;                                                     // a hit implies ref base == class base
+                if (C0 && (qq >> 31)) continue;                                         // ... and the read base must be that letter
             }
         }
-        __syncwarp();
-        if (lane == 0) S.carry_sum = sat_add(S.carry_sum, sum);
-        __syncwarp();
-        carry_cnt += n;
+        if (prob > 0xffu) { w_raise(R, kErrMLIndex); continue; }                        // src/mod.c:1174
+        const uint32_t fl = lut[prob];                                                  // src/mod.c:1181-1191
+        if (!(fl & 1u)) continue;
+        const unsigned long long inc = 1ull | ((unsigned long long)((fl >> 1) & 1u) << 32);
+        if (!EX || ins16 == 0u) {
+            unsigned long long *cell = cells + ((unsigned long long)ref_pos * per_pos + within);
+            red_add_u64(cell, inc);                                                     // the '*' stratum (or the only one)
+            if (EX && hslot) red_add_u64(cell + hslot, inc);                            // src/mod.c:906-928
+        } else {
+            pending = true; sp_pos = ref_pos; sp_meta = ins16 | (((fl >> 1) & 1u) << 16);
+        }
     }
     if (EX) {
         __syncwarp();
         w_sparse_flush(P, T, pending, nrec, (uint32_t)S.tid, rev, sp_pos, cd.outc, sp_meta & 0xffffu, S.hp, sp_meta >> 16, lane);
     }
-    // ---- '.' block: the class bases no explicit call selected are implicit calls (src/mod.c:1203-1367)
-    if (Z.dot && !dead && w_err(R) == 0u) {
-        uint32_t bound = 0xffffffffu;
-        if (bd->is_n) {                                                                     // Q8: [0,last) U (last, #N letters)
-            const uint32_t cnt_n = s_count_n(aoff, lane), last1 = carry_cnt > 0u ? S.carry_sum : 0u;
-            bound = last1 > cnt_n ? last1 : cnt_n;
-        }
-        while (Z.p_hi < Z.n_u4 && Z.cum < bound) s_append(P, aoff, jb, seq, G, Z, lane);
-        s_retire(P, aoff, jb, Z.p_ret, Z.p_hi, bound, lane);
-    }
-    return carry_cnt;
 }
 
-// the less common tails get their own functions (own register allocation, out of the hot loop's footprint)
-__device__ __noinline__ uint32_t s_block_other(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t ml_base, uint32_t lane, uint32_t tail) {
-    if (tail == 1u) return s_block<1>(P, aoff, jb, ml_base, lane);
-    if (tail == 2u) return s_block<2>(P, aoff, jb, ml_base, lane);
-    if (tail == 3u) return s_block<3>(P, aoff, jb, ml_base, lane);
-    return s_block<4>(P, aoff, jb, ml_base, lane);
+// one text tile of block jb: skip counts -> ranks -> read positions -> counts.  Returns the tile's token count.
+//   tail  0 fast C/G/T   1 fast, class A   2 fast + --insertions / --haplotypes / sampled CIGAR   3 = 1 + 2   4 general (w_call)
+__device__ __noinline__ uint32_t s_tile(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t tb, uint32_t carry_cnt, uint32_t ml_base,
+                                        uint32_t lane, uint32_t tail) {
+    const SArena A = s_arena(aoff);
+    WRead *R = A.R;
+    WTile *T = A.T;
+    WState &S = R->st;
+    const WBlock *bd = &R->blk[jb];
+    uint32_t sum = 0;
+    const uint32_t n = w_tile_ranks(R, T, tb, bd->hdr_end, bd->end, S.carry_sum, &sum, lane);
+    if (bd->any_req && n) {
+        s_select_tile(P, aoff, jb, n, lane);
+        if (tail == 0u) s_tail_fast<false, false>(P, R, T, A.s_lut, bd, n, carry_cnt, ml_base, lane);
+        else if (tail == 1u) s_tail_fast<true, false>(P, R, T, A.s_lut, bd, n, carry_cnt, ml_base, lane);
+        else if (tail == 2u) s_tail_fast<false, true>(P, R, T, A.s_lut, bd, n, carry_cnt, ml_base, lane);
+        else if (tail == 3u) s_tail_fast<true, true>(P, R, T, A.s_lut, bd, n, carry_cnt, ml_base, lane);
+        else {                                                     // several codes per block, `view`, canonical base N, slow contexts
+            const uint32_t cls = bd->cls, rd_code = (!bd->is_n && cls >= 1u && cls <= 3u) ? cls : 4u;
+            for (uint32_t c = lane; c < n; c += 32u) {
+                const uint32_t qq = T->rank[c];
+                if (qq != kNoCall) w_call(P, R, S.flex, A.s_lut, bd, jb, qq & 0x7fffffffu, false, carry_cnt + c, ml_base, rd_code);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) S.carry_sum = sat_add(S.carry_sum, sum);
+    __syncwarp();
+    return n;
+}
+
+// end of a '.' block: the class bases no explicit call selected are implicit calls (src/mod.c:1203-1367)
+__device__ __noinline__ void s_block_finish(const DecodeParams &P, uint32_t aoff, uint32_t jb, uint32_t n_calls, uint32_t lane) {
+    const SArena A = s_arena(aoff);
+    WRead *R = A.R;
+    const WState &S = R->st;
+    const WBlock *bd = &R->blk[jb];
+    SStream Z = *A.Z;
+    uint32_t bound = 0xffffffffu;
+    if (bd->is_n) {                                                // Q8: [0,last) U (last, #N letters)
+        const uint32_t cnt_n = s_count_n(aoff, lane), last1 = n_calls > 0u ? S.carry_sum : 0u;
+        bound = last1 > cnt_n ? last1 : cnt_n;
+    }
+    while (Z.p_hi < Z.n_u4 && Z.cum < bound) s_append(P, aoff, jb, S.seq, A.G, Z, lane);
+    s_retire(P, aoff, jb, Z.p_ret, Z.p_hi, bound, lane);
 }
 
 // MINB = resident CTAs per SM the register allocation is bounded for (8: 64 registers).
@@ -364,6 +391,7 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
     w_sparse_open(A.T, lane);
     WRead *R = A.R;
     uint32_t *flex = A.flex;
+    const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(SFixed)) / 4u;
     WState &S = R->st;
     for (;;) {
         uint32_t r = 0;
@@ -380,11 +408,13 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
             const uint32_t words = (uint32_t)((sizeof(WState) + sizeof(uint32_t) * (kWBlocks + 4) + sizeof(WBlock) * nb) / 4);
             for (uint32_t i = lane; i < words; i += 32u) dst[i] = src[i];
             __syncwarp();
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(S.flex_home);
-            uint4 *d4 = reinterpret_cast<uint4 *>(flex);
-            for (uint32_t i = lane; i < ((S.n_stage + 3u) >> 2); i += 32u) d4[i] = s4[i];
-            __syncwarp();
-            if (lane == 0) { S.flex = flex; S.flex_home = flex; }
+            if (S.n_stage <= flex_words) {                          // short CIGARs (HiFi): the prefix arrays move into the arena
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(S.flex_home);
+                uint4 *d4 = reinterpret_cast<uint4 *>(flex);
+                for (uint32_t i = lane; i < ((S.n_stage + 3u) >> 2); i += 32u) d4[i] = s4[i];
+                __syncwarp();
+                if (lane == 0) S.flex = flex;
+            }                                                      // else: looked up where k_flat_setup left them (HBM, L1-cached)
             __syncwarp();
         }
         // ---- blocks in order
@@ -393,11 +423,23 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
         const bool ex = P.insertions || P.haplotypes || S.cshift != 0u;
         for (uint32_t jb = 0; jb < n_blocks; ++jb) {
             const WBlock *bd = &R->blk[jb];
+            const uint32_t a0 = bd->hdr_end, a1 = bd->end;
             const uint32_t tail = !w_fast_ok(P, S, bd) ? 4u : (bd->cls == 0u ? 1u : 0u) + (ex ? 2u : 0u);
-            const uint32_t n = tail == 0u ? s_block<0>(P, aoff, jb, ml_base, lane) : s_block_other(P, aoff, jb, ml_base, lane, tail);
+            if (lane == 0) { s_stream_open(*A.Z, S, bd); S.carry_sum = 0; }
+            __syncwarp();
+            uint32_t carry_cnt = 0;
+            for (uint32_t tb = a0 & ~15u; tb < a1; tb += (uint32_t)kWChunks * 16u) {
+                carry_cnt += s_tile(P, aoff, jb, tb, carry_cnt, ml_base, lane, tail);
+                if (*reinterpret_cast<volatile uint32_t *>(&S.err)) break;      // (re-read converged below)
+            }
             err = w_err(R);
             if (err) break;
-            if (n > 0u) ml_base += n * bd->K;                      // src/mod.c:1200
+            if (bd->dot && bd->any_req) {
+                s_block_finish(P, aoff, jb, carry_cnt, lane);
+                err = w_err(R);
+                if (err) break;
+            }
+            if (carry_cnt > 0u) ml_base += carry_cnt * bd->K;      // src/mod.c:1200
         }
         if (err) w_report(P, S.r, err, lane);
     }

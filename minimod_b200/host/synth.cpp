@@ -55,7 +55,8 @@ static SynthConfig config_of(int id) {
     }
 }
 
-struct Contig { std::string name; std::string seq; std::vector<std::pair<uint32_t, uint32_t>> mappable; uint64_t mappable_len = 0; };
+struct Contig { std::string name; std::string seq; std::vector<std::pair<uint32_t, uint32_t>> mappable; uint64_t mappable_len = 0;
+                uint32_t gid = 0; uint64_t read_base = 0, n_reads = 0; };   // gid: job-wide contig id (seeds); reads [read_base, read_base + n_reads)
 
 class Synth {
 public:
@@ -65,22 +66,32 @@ public:
     uint64_t total_mappable = 0;
     uint64_t n_reads = 0;
 
-    void build_reference(const std::vector<std::pair<std::string, uint32_t>> &table) {
+    // Every contig is generated from (seed, gid) alone -- its sequence and its reads -- so a job is the same set of
+    // reads however its contigs are dealt to instances (contig sharding across GPUs).
+    void build_reference(const std::vector<std::pair<std::string, uint32_t>> &table, const uint32_t *gids) {
         contigs.resize(table.size());
+        for (size_t ci = 0; ci < table.size(); ++ci) contigs[ci].gid = gids ? gids[ci] : (uint32_t)ci;
         std::vector<std::thread> th;
-        for (size_t ci = 0; ci < table.size(); ++ci) th.emplace_back([this, ci, &table]() { gen_contig(ci, table[ci].first, table[ci].second); });
+        const size_t nt = std::max<size_t>(1, std::min<size_t>(table.size(), std::thread::hardware_concurrency() ? std::thread::hardware_concurrency() : 8));
+        for (size_t t = 0; t < nt; ++t)
+            th.emplace_back([this, t, nt, &table]() { for (size_t ci = t; ci < table.size(); ci += nt) gen_contig(ci, table[ci].first, table[ci].second); });
         for (auto &t : th) t.join();
         total_mappable = 0;
-        for (auto &c : contigs) total_mappable += c.mappable_len;
-        double mean_len = cfg.len_model == 1 ? cfg.len_b : cfg.len_a;
-        n_reads = (uint64_t)(cfg.coverage * (double)total_mappable / mean_len);
+        const double mean_len = cfg.len_model == 1 ? cfg.len_b : cfg.len_a;
+        n_reads = 0;
+        for (auto &c : contigs) {
+            total_mappable += c.mappable_len;
+            c.read_base = n_reads;
+            c.n_reads = (uint64_t)(cfg.coverage * (double)c.mappable_len / mean_len);
+            n_reads += c.n_reads;
+        }
     }
 
     void gen_contig(size_t ci, const std::string &name, uint32_t len) {
         Contig &c = contigs[ci];
         c.name = name;
         c.seq.resize(len);
-        Rng r(seed * 1000003ull + ci * 7919ull + 17);
+        Rng r(seed * 1000003ull + (uint64_t)c.gid * 7919ull + 17);
         char *s = &c.seq[0];
         for (uint32_t i = 0; i < len; ++i) {
             uint32_t u = r.below(100);
@@ -103,7 +114,15 @@ public:
 
     // read `idx` (0..n_reads-1), coordinate-sorted by construction (stratified uniform starts)
     void make_read(uint64_t idx, BamRecord *rec) const {
-        Rng r(seed ^ Rng::mix(idx * 2 + 1));
+        size_t ci = 0, iv = 0;
+        {
+            size_t lo = 0, hi = contigs.size();                 // last contig with read_base <= idx (coordinate order == index order)
+            while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (contigs[mid].read_base <= idx) lo = mid; else hi = mid; }
+            ci = lo;
+        }
+        const Contig &c = contigs[ci];
+        const uint64_t j = idx - c.read_base;                   // the contig's j-th read
+        Rng r(seed ^ Rng::mix(((uint64_t)c.gid + 1) * 0x9e3779b97f4a7c15ull + j * 2 + 1));
         // ---- length
         uint32_t L;
         if (cfg.len_model == 0) { double v = cfg.len_a + cfg.len_b * r.normal(); L = (uint32_t)std::max<double>(cfg.len_lo, std::min<double>(cfg.len_hi, v)); }
@@ -112,16 +131,10 @@ public:
             double v = exp(mu + sigma * r.normal());
             L = (uint32_t)std::max<double>(cfg.len_lo, std::min<double>(cfg.len_hi, v));
         } else L = (uint32_t)cfg.len_a;
-        // ---- start: stratum idx of the concatenated mappable space
-        double frac = ((double)idx + r.uniform()) / (double)n_reads;
-        uint64_t off = (uint64_t)(frac * (double)total_mappable);
-        size_t ci = 0, iv = 0;
-        for (ci = 0; ci < contigs.size(); ++ci) {
-            if (off < contigs[ci].mappable_len) break;
-            off -= contigs[ci].mappable_len;
-        }
-        if (ci == contigs.size()) { ci = contigs.size() - 1; off = contigs[ci].mappable_len - 1; }
-        const Contig &c = contigs[ci];
+        // ---- start: stratum j of the contig's mappable space
+        double frac = ((double)j + r.uniform()) / (double)std::max<uint64_t>(1, c.n_reads);
+        uint64_t off = (uint64_t)(frac * (double)c.mappable_len);
+        if (off >= c.mappable_len) off = c.mappable_len ? c.mappable_len - 1 : 0;
         for (iv = 0; iv < c.mappable.size(); ++iv) {
             uint32_t l = c.mappable[iv].second - c.mappable[iv].first;
             if (off < l) break;
@@ -249,15 +262,19 @@ typedef struct {
 } mmh_synth_stats_t;
 
 // contig_names/lens: the header table; the reference sequence is generated for every contig.
-void *mmh_synth_new(int config_id, uint64_t seed, int n_contigs, const char *const *names, const uint32_t *lens, double coverage) {
+// gids (optional): job-wide ids of the contigs; a contig's sequence and reads depend on (seed, gid) only.
+void *mmh_synth_new2(int config_id, uint64_t seed, int n_contigs, const char *const *names, const uint32_t *lens, const uint32_t *gids, double coverage) {
     Synth *s = new Synth();
     s->cfg = config_of(config_id);
     if (coverage > 0) s->cfg.coverage = coverage;
     s->seed = seed;
     std::vector<std::pair<std::string, uint32_t>> table;
     for (int i = 0; i < n_contigs; ++i) table.push_back({names[i], lens[i]});
-    s->build_reference(table);
+    s->build_reference(table, gids);
     return s;
+}
+void *mmh_synth_new(int config_id, uint64_t seed, int n_contigs, const char *const *names, const uint32_t *lens, double coverage) {
+    return mmh_synth_new2(config_id, seed, n_contigs, names, lens, nullptr, coverage);
 }
 void mmh_synth_free(void *h) { delete (Synth *)h; }
 uint64_t mmh_synth_n_reads(void *h) { return ((Synth *)h)->n_reads; }

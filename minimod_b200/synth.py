@@ -30,14 +30,17 @@ def cli_args(config):
 
 
 class Synth:
-    def __init__(self, config, contigs=(("chr22", CHR22_LEN),), coverage=0.0, seed=None):
+    def __init__(self, config, contigs=(("chr22", CHR22_LEN),), coverage=0.0, seed=None, gids=None):
+        """gids: job-wide ids of `contigs` (default 0..n-1).  A contig's sequence and reads depend on (seed, gid) only,
+        so the union over any split of a contig table into instances is the same job (contig sharding)."""
         self.host = N.load_host()
         self.config = config
         self.names = [n.encode() for n, _ in contigs]
         self.lens = [l for _, l in contigs]
         names = (C.c_char_p * len(contigs))(*self.names)
         lens = (C.c_uint32 * len(contigs))(*self.lens)
-        self.h = self.host.mmh_synth_new(config, SEED0 + config if seed is None else seed, len(contigs), names, lens, coverage)
+        g = (C.c_uint32 * len(contigs))(*(gids if gids is not None else range(len(contigs))))
+        self.h = self.host.mmh_synth_new2(config, SEED0 + config if seed is None else seed, len(contigs), names, lens, g, coverage)
         self.n_reads = self.host.mmh_synth_n_reads(self.h)
 
     def ref(self, tid):
