@@ -244,6 +244,8 @@ int  mmc_touched_range(mmc_ctx *ctx, int32_t tid, uint32_t *lo, uint32_t *hi);
 
 int  mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out);
 int  mmc_reset_timers(mmc_ctx *ctx);
+/* one line naming the kernels the decode stage of this context launches (measurement reports) */
+const char *mmc_describe(mmc_ctx *ctx);
 /* per-launch device time (ms) of the most recent decode kernel on `batch` */
 int  mmc_last_decode_ms(mmc_ctx *ctx, mmc_batch_t *batch, double *ms);
 

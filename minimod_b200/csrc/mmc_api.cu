@@ -65,6 +65,7 @@ struct Slot {
     bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false;
     uint32_t n_reads_submitted = 0;
     uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
+    bool use_stream = false;                   // this batch goes through k_decode_stream (long CIGARs / long reads) instead of k_decode_warp<PRE>
     int s_ctas = 8; uint32_t s_arena = 0, s_setup_flex = 4608;   // k_decode_stream: CTAs per SM, arena bytes per warp; k_flat_setup's room for dir | cq | cr
 };
 
@@ -84,7 +85,7 @@ struct mmc_ctx {
     std::vector<mmc_mod_t> mods;
     std::vector<ContigHost> contigs;
     std::vector<Slot> slots;
-    std::string err;
+    std::string err, desc;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
     int seq_packing = 4;                                             // opts.seq_packing, or MMC_SEQ_PACKING
     int stream_path = 1;                       // k_flat_setup + k_decode_stream (default): streaming merge, constant shared memory per warp
@@ -107,6 +108,7 @@ struct mmc_ctx {
     SparseRec *d_sparse = nullptr;
     unsigned long long *d_sparse_n = nullptr;
     uint64_t sparse_cap = 0, view_cap = 0;
+    uint64_t sparse_seen = 0;                  // highest fill level of the side buffer any finished batch reported
     bool committed = false;
     cudaStream_t fin_stream = nullptr;
     cudaEvent_t ev_f0 = nullptr, ev_f1 = nullptr;
@@ -282,7 +284,11 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
         while (mb > 1 && (ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed)) / 4u < p95) --mb;
     }
     s.max_cig = max_cig; s.max_l = max_l; s.pool_need = pool_need; s.variant = mb;
-    if (ctx->stream_path) {
+    // Two implementations of the stage: k_decode_warp<MINB,PRE> keeps a read's rank index and CIGAR arrays in its arena -- fewest
+    // instructions while three CTAs fit an SM (HiFi: 15 kb reads, ~30 CIGAR ops) -- and k_decode_stream needs constant shared
+    // memory per warp whatever the read (ONT CIGARs, 50 kb reads: 24 warps per SM where the former drops to 16 or 8).
+    s.use_stream = ctx->stream_path == 2 || (ctx->stream_path == 1 && mb < 3);
+    if (s.use_stream) {
         // k_decode_stream: constant arena per warp (SFixed + room for the dir | cq | cr of short CIGARs; longer ones are
         // looked up in the pool k_flat_setup wrote).  k_flat_setup builds the arrays in its own arena: sized for ~95 % of
         // the reads un-sampled (the rest get every 2nd / 4th ... op, w_setup_read).
@@ -293,9 +299,13 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
             std::nth_element(need.begin(), need.begin() + k, need.end());
             p95 = need[k];
         }
+        (void)p95;
         s.s_ctas = ctx->s_minb;
-        s.s_arena = (uint32_t)((sizeof(SFixed) + 1024 + 15) & ~(size_t)15);
-        s.s_setup_flex = std::min<uint32_t>(std::max<uint32_t>(4608u, (p95 * 4u + 15u) & ~15u), 24576u);
+        s.s_arena = (uint32_t)((sizeof(SFixed) + 15) & ~(size_t)15);
+        s.s_setup_flex = 256;                      // stream mode: k_flat_setup writes the CIGAR table straight into the pool
+        uint64_t need_s = 0;
+        for (uint32_t i = 0; i < n; ++i) need_s += (((uint64_t)(b.l_seq[i] >> 5) + 2u + 3u) & ~3ull) + 2ull * std::max<uint32_t>(1u, b.n_cigar[i]) + 4u;
+        s.pool_need = std::max<uint64_t>(s.pool_need, need_s);
     }
 }
 
@@ -344,9 +354,43 @@ int upload(mmc_ctx *ctx, Slot &s) {
     return MMC_OK;
 }
 
+int wait_slot(mmc_ctx *ctx, Slot &s);
+
+// The side buffer holds the whole run's sparse records (the reference's hash map has no limit either): before a batch is
+// launched, make sure every batch that can be in flight still fits behind the highest fill level seen so far, and grow the
+// buffer (all slots drained, device-to-device copy) when it does not.  A single batch that appends more than its reserve
+// is caught in wait_slot().
+int reserve_sparse(mmc_ctx *ctx, const Slot &s) {
+    if (ctx->opts.subtool != MMC_FREQ) return MMC_OK;
+    if (!ctx->opts.insertions && !ctx->opts.haplotypes && ctx->wild_req < 0) return MMC_OK;   // every cell is dense
+    const mmc_batch_t &b = s.pub;
+    // appends of one batch: <= 2 records per explicit call (haplotype stratum + '*') + implicit calls inside insertions
+    const uint64_t per_batch = 4 * b.ml_used + b.seq_used / 4 + (1u << 16);
+    const uint64_t need = ctx->sparse_seen + per_batch * (uint64_t)ctx->slots.size();
+    if (need <= ctx->sparse_cap) return MMC_OK;
+    for (Slot &o : ctx->slots) { int rc = wait_slot(ctx, o); if (rc != MMC_OK) return rc; }
+    const uint64_t again = ctx->sparse_seen + per_batch * (uint64_t)ctx->slots.size();
+    if (again <= ctx->sparse_cap) return MMC_OK;
+    uint64_t cap = ctx->sparse_cap;
+    while (cap < again) cap += cap / 2 + (1u << 20);
+    SparseRec *nb = nullptr;
+    if (cudaMalloc((void **)&nb, sizeof(SparseRec) * cap) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MMC_ENOMEM, "cannot grow the sparse count buffer to %llu records (%.1f GB)", (unsigned long long)cap, cap * 16 / 1e9);
+    }
+    unsigned long long sn = 0;
+    CU(ctx, cudaMemcpy(&sn, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost));
+    if (sn > ctx->sparse_cap) sn = ctx->sparse_cap;
+    if (sn) CU(ctx, cudaMemcpy(nb, ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToDevice));
+    CU(ctx, cudaFree(ctx->d_sparse));
+    ctx->d_sparse = nb; ctx->sparse_cap = cap;
+    return MMC_OK;
+}
+
 int launch_decode(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const uint32_t n = s.n_reads_submitted;
+    { int rc = reserve_sparse(ctx, s); if (rc != MMC_OK) return rc; }
     // reset the slot's device state: err = ~0, view_n = 0, work counters and deferred count = 0
     // layout: u64 [0] err, [1] view_n, [4] pool cursor; u32 [4] work counter of k_decode_warp, [5] reads it defers,
     // [6] work counter of k_decode, [7] reads the flat path defers, [10] tiles, [11] reads with '.' blocks
@@ -418,8 +462,8 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     }
 
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
-    if (ctx->stream_path) {
-        // default: k_flat_setup prepares every read (state + CIGAR arrays in HBM), k_decode_stream merges the calls
+    if (s.use_stream) {
+        // k_flat_setup prepares every read (state + CIGAR table in HBM), k_decode_stream merges the calls
         // against the SEQ stream; what k_flat_setup cannot prepare goes down the chain below
         const uint32_t setup_arena = kWReadBytes + s.s_setup_flex;
         F.arena_bytes = setup_arena; F.consumer_flex_words = 1u << 24; F.read_count = n; F.stream = 1;
@@ -447,7 +491,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         if (wgrid == 0) wgrid = 1;
         const size_t wsmem = (size_t)kWHeadBytes + (size_t)w_arena_bytes * (kWThreads / 32);
         PreParams Q; Q.reads = nullptr; Q.n = 0;
-        if (ctx->split_path && !ctx->stream_path) {
+        if (ctx->split_path && !s.use_stream) {
             // split path: k_flat_setup prepares every read (state + CIGAR arrays in HBM), the fused kernel does the rest
             F.arena_bytes = setup_arena_bytes;
             F.consumer_flex_words = (w_arena_bytes - (uint32_t)sizeof(WFixed)) / 4u;
@@ -479,6 +523,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(s.ev_k1, s.stream));
     CU(ctx, cudaMemcpyAsync(s.h_state, s.d_state, 32, cudaMemcpyDeviceToHost, s.stream));
+    CU(ctx, cudaMemcpyAsync(s.h_state + 8, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost, s.stream));   // fill level of the side buffer
     ctx->tm.kernel_launches += 1;
     ctx->tm.batches += 1;
     ctx->tm.reads += n;
@@ -501,6 +546,12 @@ int wait_slot(mmc_ctx *ctx, Slot &s) {
         ctx->tm.deferred_reads += ((const uint32_t *)s.h_state)[5];
         ctx->tm.flat_deferred_reads += ((const uint32_t *)s.h_state)[7];
         s.timed = false;
+    }
+    if (s.n_reads_submitted) {
+        ctx->sparse_seen = std::max<uint64_t>(ctx->sparse_seen, s.h_state[8]);
+        if (s.h_state[8] > ctx->sparse_cap)
+            return fail(ctx, MMC_ENOMEM, "sparse count buffer overflow (%llu records > capacity %llu) inside one batch; raise sparse_capacity (minimod: --sparse-cap) or lower -K/-B",
+                        (unsigned long long)s.h_state[8], (unsigned long long)ctx->sparse_cap);
     }
     if (s.n_reads_submitted && s.h_state[0] != ~0ull) {
         uint32_t read = (uint32_t)(s.h_state[0] >> 32), code = (uint32_t)(s.h_state[0] & 0xffffffffu);
@@ -554,7 +605,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->split_path = 0; ctx->stream_path = 0; }
         else if (!strcmp(e, "warp")) { ctx->split_path = 0; ctx->stream_path = 0; }
         else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
-        else if (!strcmp(e, "stream")) ctx->stream_path = 1;
+        else if (!strcmp(e, "stream")) ctx->stream_path = 2;          // always (default 1: per batch, by the reads' shape)
     }
     if (const char *e = getenv("MMC_STREAM_MINB")) { int v = atoi(e); if (v == 8 || v == 6 || v == 5 || v == 4) ctx->s_minb = v; }   // tuning
     ctx->s_head = (uint32_t)std::min<int>(opts->n_mods, kWLutSlots) * 256u;
@@ -666,7 +717,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     CUC(cudaMalloc((void **)&ctx->d_touch, sizeof(int32_t) * 2 * nc));
 
     // ---- side buffers
-    ctx->sparse_cap = o.sparse_capacity ? o.sparse_capacity : (o.subtool == MMC_FREQ ? std::max<uint64_t>(1u << 20, o.max_bytes / 8) : 16);
+    ctx->sparse_cap = o.sparse_capacity ? o.sparse_capacity : (o.subtool == MMC_FREQ ? std::max<uint64_t>(1u << 20, o.max_bytes / 8) : 16);   // starting size: grows (reserve_sparse)
     CUC(cudaMalloc((void **)&ctx->d_sparse, sizeof(SparseRec) * ctx->sparse_cap));
     CUC(cudaMalloc((void **)&ctx->d_sparse_n, 8));
     CUC(cudaMemset(ctx->d_sparse_n, 0, 8));
@@ -1261,6 +1312,7 @@ int mmc_freq_reset(mmc_ctx *ctx) {
     if (nc) CU(ctx, cudaMemcpyAsync(ctx->d_touch, touch.data(), sizeof(int32_t) * 2 * nc, cudaMemcpyHostToDevice, ctx->fin_stream));
     CU(ctx, cudaMemsetAsync(ctx->d_sparse_n, 0, 8, ctx->fin_stream));
     CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    ctx->sparse_seen = 0;
     return MMC_OK;
 }
 
@@ -1341,6 +1393,24 @@ int mmc_touched_range(mmc_ctx *ctx, int32_t tid, uint32_t *lo, uint32_t *hi) {
     CU(ctx, cudaMemcpy(&h, ctx->d_touch + nc + tid, 4, cudaMemcpyDeviceToHost));
     if (l >= h) { *lo = 0; *hi = 0; } else { *lo = (uint32_t)l; *hi = (uint32_t)h; }
     return MMC_OK;
+}
+
+const char *mmc_describe(mmc_ctx *ctx) {
+    if (!ctx) return "";
+    char buf[256];
+    bool any_stream = false, any_split = false;
+    for (const Slot &sl : ctx->slots) { if (sl.uploaded || sl.in_flight || sl.n_reads_submitted) { if (sl.use_stream) any_stream = true; else any_split = true; } }
+    if (ctx->stream_path && any_stream && !any_split)
+        snprintf(buf, sizeof(buf), "k_flat_setup + k_decode_stream<%d> (dominant) + the fallback kernels k_decode_warp<%d,0> / k_decode for deferred reads",
+                 ctx->s_minb, ctx->w_minb);
+    else if (ctx->stream_path && any_stream)
+        snprintf(buf, sizeof(buf), "k_flat_setup + k_decode_stream<%d> or k_decode_warp<MINB,PRE> per batch (by read shape) + fallback kernels", ctx->s_minb);
+    else if (ctx->warp_path && ctx->split_path)
+        snprintf(buf, sizeof(buf), "k_flat_setup + k_decode_warp<MINB,PRE> (dominant; MINB per batch, default %d) + k_decode_warp<MINB,0> / k_decode for deferred reads", ctx->w_minb);
+    else if (ctx->warp_path) snprintf(buf, sizeof(buf), "k_decode_warp<MINB,0> + k_decode for deferred reads");
+    else snprintf(buf, sizeof(buf), "k_decode (CTA per read)");
+    ctx->desc = buf;
+    return ctx->desc.c_str();
 }
 
 int mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out) {

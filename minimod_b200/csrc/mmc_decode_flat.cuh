@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant_
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < F.read_count; r += n_warps) {
         WRead *G = &F.reads[r];
         __syncwarp();
-        bool ok = w_setup_read<false>(P, aoff, F.consumer_flex_words, local_words, F.defer_list, F.defer_n, r, lane, F.stream);
+        bool ok = w_setup_read<false>(P, aoff, F.consumer_flex_words, local_words, F.defer_list, F.defer_n, r, lane, F.stream ? &F.fa : nullptr);
         __syncwarp();
         unsigned long long base = 0;
-        const uint32_t take = ok ? A.R->st.n_stage : 0u;
-        if (ok) {                                                           // CIGAR arrays -> pool
+        const uint32_t take = (ok && !F.stream) ? A.R->st.n_stage : 0u;     // (stream mode: the table was written in place)
+        if (ok && !F.stream) {                                              // CIGAR arrays -> pool
             if (lane == 0) base = atomicAdd(F.fa.cursor, (unsigned long long)take);
             base = ((unsigned long long)__shfl_sync(kFull, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)base, 0);
             if (base + take > F.fa.cap) { w_defer(F.defer_list, F.defer_n, r, lane); ok = false; }
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kFThreads) k_flat_setup(const __grid_constant_
         uint32_t *dst = reinterpret_cast<uint32_t *>(G);
         for (uint32_t i = lane; i < words; i += 32u) dst[i] = src[i];
         __syncwarp();
-        if (lane == 0) { G->st.flex = F.fa.pool + base; G->st.flex_home = F.fa.pool + base; }
+        if (lane == 0 && !F.stream) { G->st.flex = F.fa.pool + base; G->st.flex_home = F.fa.pool + base; }
     }
 }
 

@@ -29,6 +29,7 @@ namespace mmc {
 
 constexpr int kSThreads = 128;               // 4 warps per CTA: fine-grained residency
 constexpr uint32_t kSRing = 128u, kSMask = kSRing - 1u;
+constexpr uint32_t kSWindow = 96u;           // searchable positions behind p_hi (the other 32 slots receive the next chunk)
 
 struct SRing {
     uint4    vec[kSRing];                    // SEQ vector of stream position p at slot p & kSMask
@@ -43,19 +44,19 @@ struct SStream {
     uint32_t p_ret;                          // '.' blocks: vectors before it have emitted their implicit calls
     uint32_t mode, pat;                      // 0: nibble == pat, 1: class A (everything but C,G,T,N), 2: every base (canonical base N)
     uint32_t n_u4, tail_n, rev, dot;
+    uint32_t pf_on, pf_ph;                   // a bulk copy of the vectors [p_hi, p_hi + 32) is in flight / landed; parity of the warp's mbarrier
 };
 
-struct SFixed { WRead rd; WTile tl; SRing rg; SStream zs; uint32_t pad[2]; };
-static_assert(sizeof(SFixed) % 16 == 0, "arena pieces are 16-byte aligned");
-struct SArena { uint8_t *s_lut; WRead *R; WTile *T; SRing *G; SStream *Z; uint32_t *flex; };
+struct SFixed { WRead rd; WTile tl; SRing rg; SStream zs; unsigned long long bar; };
+static_assert(sizeof(SFixed) % 16 == 0 && offsetof(SFixed, rg) % 16 == 0, "arena pieces are 16-byte aligned");
+struct SArena { uint8_t *s_lut; WRead *R; WTile *T; SRing *G; SStream *Z; unsigned long long *bar; };
 __device__ __forceinline__ SArena s_arena(uint32_t aoff) {
     MMC_DYN_SMEM(uint4, w_dyn);
     uint8_t *base = reinterpret_cast<uint8_t *>(w_dyn);
     SArena A;
     A.s_lut = base;
     SFixed *sf = reinterpret_cast<SFixed *>(base + aoff);
-    A.R = &sf->rd; A.T = &sf->tl; A.G = &sf->rg; A.Z = &sf->zs;
-    A.flex = reinterpret_cast<uint32_t *>(base + aoff + (uint32_t)sizeof(SFixed));
+    A.R = &sf->rd; A.T = &sf->tl; A.G = &sf->rg; A.Z = &sf->zs; A.bar = &sf->bar;
     return A;
 }
 
@@ -84,12 +85,41 @@ __device__ __forceinline__ uint32_t s_mask8(uint32_t f) {
     return (y * 0x01041040u) >> 24;
 }
 
-__device__ __forceinline__ void s_stream_open(SStream &Z, const WState &S, const WBlock *bd) {
+// The SEQ stream is fed by bulk asynchronous copies (cp.async.bulk -> UBLKCP, completing on the warp's mbarrier): the 32
+// vectors the next count step will look at are already on their way into the ring while the current round of calls is
+// searched, selected and mapped.  Reverse reads stream from the end of SEQ: a chunk lands in memory order, so position p
+// sits at slot (p & kSMask) ^ 31 (pre / exp stay at p & kSMask).
+__device__ __forceinline__ uint32_t s_vslot(const SStream &Z, uint32_t p) { return (p & kSMask) ^ (Z.rev ? 31u : 0u); }
+__device__ __forceinline__ void s_prefetch(const uint8_t *seq, SRing *G, unsigned long long *bar, SStream &Z, uint32_t lane) {
+    if (Z.p_hi >= Z.n_u4) return;
+    const uint32_t p0 = Z.p_hi, cnt = Z.n_u4 - p0 < 32u ? Z.n_u4 - p0 : 32u;
+    __syncwarp();                                                  // every lane is done with the slots about to be overwritten
+    if (lane == 0) {
+        const uint32_t u_lo = Z.rev ? Z.n_u4 - p0 - cnt : p0;
+        mmc_bulk_g2s(&G->vec[(p0 & kSMask) + (Z.rev ? 32u - cnt : 0u)], seq + (size_t)u_lo * 16u, cnt * 16u, bar);
+    }
+    Z.pf_on = 1u;
+}
+__device__ __forceinline__ void s_prefetch_wait(unsigned long long *bar, SStream &Z) {
+    if (Z.pf_on) { mmc_mbar_wait(bar, Z.pf_ph); Z.pf_ph ^= 1u; Z.pf_on = 0u; }
+}
+
+// start of block jb: reset the stream (a copy a previous block left in flight is drained first) and start fetching its head
+__device__ __noinline__ void s_open_block(uint32_t aoff, uint32_t jb, uint32_t lane) {
+    const SArena A = s_arena(aoff);
+    WState &S = A.R->st;
+    const WBlock *bd = &A.R->blk[jb];
+    SStream Z = *A.Z;
+    s_prefetch_wait(A.bar, Z);
     Z.p_hi = 0; Z.cum = 0; Z.p_cov = 0; Z.p_ret = 0;
     Z.mode = bd->is_n ? 2u : bd->cls == 0u ? 1u : 0u;
     Z.pat = class_pat(bd->cls);
     Z.n_u4 = S.n_u4; Z.tail_n = (S.L & 31u) ? (S.L & 31u) : 32u; Z.rev = S.rev;
     Z.dot = (bd->dot && bd->any_req) ? 1u : 0u;
+    if (bd->any_req) s_prefetch(S.seq, A.G, A.bar, Z, lane);
+    __syncwarp();
+    if (lane == 0) { *A.Z = Z; S.carry_sum = 0; }
+    __syncwarp();
 }
 
 // implicit calls of the vectors at stream positions [p_from, p_to) of a '.' block: every class base that no
@@ -106,7 +136,7 @@ __device__ __noinline__ void s_retire(const DecodeParams &P, uint32_t aoff, uint
     __syncwarp();                                                  // the explicit bits other lanes set are visible
     for (uint32_t p = p_from + lane; p < p_to; p += 32u) {
         const uint32_t sl = p & kSMask, u = rev ? n_u4 - 1u - p : p;
-        const SVecFlags F = s_vec_flags(G->vec[sl], mode, pat, u == n_u4 - 1u ? tail_n : 32u);
+        const SVecFlags F = s_vec_flags(G->vec[sl ^ (rev ? 31u : 0u)], mode, pat, u == n_u4 - 1u ? tail_n : 32u);
         const uint32_t m32 = s_mask8(F.f0) | (s_mask8(F.f1) << 8) | (s_mask8(F.f2) << 16) | (s_mask8(F.f3) << 24);
         uint32_t imp = m32 & ~G->exp[sl];
         const uint32_t pre = G->pre[sl], tot = (uint32_t)__popc(m32);
@@ -134,21 +164,19 @@ __device__ __noinline__ uint32_t s_count_n(uint32_t aoff, uint32_t lane) {
     return __shfl_sync(kFull, warp_incl_scan(c, lane), 31);
 }
 
-// one count step: the next 32 vectors of the stream -> ring.  For '.' blocks the slots they overwrite are retired first.
-__device__ __forceinline__ void s_append(const DecodeParams &P, uint32_t aoff, uint32_t jb, const uint8_t *seq, SRing *G, SStream &Z, uint32_t lane) {
-    if (Z.dot && Z.p_hi + 32u > Z.p_ret + kSRing) {
-        const uint32_t to = Z.p_hi + 32u - kSRing;
-        s_retire(P, aoff, jb, Z.p_ret, to, 0xffffffffu, lane);
-        Z.p_ret = to;
-    }
+// one count step: the 32 vectors the last prefetch brought in are counted and join the searchable window; the next 32 are
+// requested.  The copy overwrites the vec slots of positions [p_hi - 96, p_hi - 64) (new p_hi): callers keep the window
+// they search inside the last 96 positions, and '.' blocks retire what falls out first.
+__device__ __forceinline__ void s_append(const DecodeParams &P, uint32_t aoff, uint32_t jb, const uint8_t *seq, SRing *G, unsigned long long *bar,
+                                         SStream &Z, uint32_t lane) {
+    s_prefetch_wait(bar, Z);
     const uint32_t p = Z.p_hi + lane;
     uint32_t c = 0;
     if (p < Z.n_u4) {
         const uint32_t u = Z.rev ? Z.n_u4 - 1u - p : p;
-        const uint4 v = ld16(seq + (size_t)u * 16u);
+        const uint4 v = G->vec[s_vslot(Z, p)];
         const SVecFlags F = s_vec_flags(v, Z.mode, Z.pat, u == Z.n_u4 - 1u ? Z.tail_n : 32u);
         c = (uint32_t)(__popc(F.f0) + __popc(F.f1) + __popc(F.f2) + __popc(F.f3));
-        G->vec[p & kSMask] = v;
     }
     const uint32_t incl = warp_incl_scan(c, lane);
     if (p < Z.n_u4) {
@@ -158,6 +186,12 @@ __device__ __forceinline__ void s_append(const DecodeParams &P, uint32_t aoff, u
     Z.cum += __shfl_sync(kFull, incl, 31);
     Z.p_hi = Z.p_hi + 32u < Z.n_u4 ? Z.p_hi + 32u : Z.n_u4;
     __syncwarp();
+    if (Z.dot && Z.p_hi + 32u > Z.p_ret + kSRing) {
+        const uint32_t to = Z.p_hi + 32u - kSRing;
+        s_retire(P, aoff, jb, Z.p_ret, to, 0xffffffffu, lane);
+        Z.p_ret = to;
+    }
+    s_prefetch(seq, G, bar, Z, lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -178,21 +212,21 @@ __device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff,
         const uint32_t c = c0 + lane;
         const uint32_t k = c < n ? T->rank[c] : 0xffffffffu;       // base rank == stream rank (src/mod.c:1098,1109-1113)
         const uint32_t k0 = __shfl_sync(kFull, k, 0);
-        while (Z.cum <= k0 && Z.p_hi < Z.n_u4) { const uint32_t at = Z.p_hi; s_append(P, aoff, jb, seq, G, Z, lane); Z.p_cov = at; }
+        while (Z.cum <= k0 && Z.p_hi < Z.n_u4) { const uint32_t at = Z.p_hi; s_append(P, aoff, jb, seq, G, A.bar, Z, lane); Z.p_cov = at; }
         if (Z.cum <= k0) {                                         // src/mod.c:1116: more skips than bases of the class
             w_raise(R, kErrMMRank);
             for (uint32_t x = c; x < n; x += 32u) T->rank[x] = kNoCall;
             break;
         }
         const uint32_t klast = __shfl_sync(kFull, k, (int)(n - c0 < 32u ? n - c0 - 1u : 31u));
-        while (Z.cum <= klast && Z.p_hi < Z.n_u4 && Z.p_hi + 32u <= Z.p_cov + kSRing) s_append(P, aoff, jb, seq, G, Z, lane);
+        while (Z.cum <= klast && Z.p_hi < Z.n_u4 && Z.p_hi + 32u <= Z.p_cov + kSWindow) s_append(P, aoff, jb, seq, G, A.bar, Z, lane);
         const bool act = k < Z.cum;
         const uint32_t am = __ballot_sync(kFull, act);
         c0 += (uint32_t)__popc(am);
         uint32_t p = Z.p_cov;
         if (act) {                                                 // largest p in [p_cov, p_hi) with pre[p] <= k
 #pragma unroll
-            for (uint32_t st = kSRing / 2u; st; st >>= 1) {
+            for (uint32_t st = 64u; st; st >>= 1) {                 // (window <= kSWindow = 96 < 128)
                 const uint32_t t = p + st;
                 if (t < Z.p_hi && G->pre[t & kSMask] <= k) p = t;
             }
@@ -200,7 +234,7 @@ __device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff,
         Z.p_cov = __shfl_sync(kFull, p, 31 - __clz((int)am));      // the next round's first call lies at or after this vector
         if (!act) continue;
         const uint32_t sl = p & kSMask, u = Z.rev ? Z.n_u4 - 1u - p : p;
-        const uint4 v = G->vec[sl];
+        const uint4 v = G->vec[s_vslot(Z, p)];
         uint32_t rem = k - G->pre[sl];
         const SVecFlags F = s_vec_flags(v, Z.mode, Z.pat, u == Z.n_u4 - 1u ? Z.tail_n : 32u);
         const uint32_t s0 = (uint32_t)__popc(F.f0), s1 = s0 + (uint32_t)__popc(F.f1), s2 = s1 + (uint32_t)__popc(F.f2);
@@ -238,8 +272,9 @@ template <bool C0, bool EX>
 __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, const WBlock *bd,
                                             uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
-    const uint32_t *flex = S.flex;                                 // dir | cq | cr: the arena's copy, or (long CIGARs) the pool in HBM through L1
-    const uint32_t *dir = flex + S.o_dir, *cq = flex + S.o_cq, *cr = flex + S.o_cr;
+    const uint32_t *flex = S.flex;                                 // dir | {cq, cr}: where k_flat_setup wrote them (HBM, read through L1)
+    const uint32_t *dir = flex + S.o_dir;
+    const uint2 *pr = reinterpret_cast<const uint2 *>(flex + S.o_cq);
     const uint32_t rev = S.rev, total_q = S.total_q, g = S.gshift, last_samp = S.n_samp - 1u, ml_len = S.ml_len, ref_len = S.ref_len;
     const int32_t pos = S.pos;
     const uint8_t *ml = S.ml;
@@ -283,13 +318,14 @@ __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTi
         } else {
             if (q >= total_q) continue;
             const uint32_t b = q >> g;
-            uint32_t lo = dir[b], hi = (((b + 1u) << g) < total_q) ? dir[b + 1u] : last_samp;
+            uint32_t lo = ldg32(dir + b), hi = (((b + 1u) << g) < total_q) ? ldg32(dir + b + 1u) : last_samp;
             const uint32_t qlim = (q + 1u) << 4;
-            while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (cq[mid] < qlim) lo = mid; else hi = mid - 1u; }
-            const uint32_t ce = cq[lo], op = ce & 15u;
-            if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(cr[lo] + q - (ce >> 4)));
+            while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (ldg32(&pr[mid].x) < qlim) lo = mid; else hi = mid - 1u; }   // 32-base buckets: a step or none
+            const uint2 en = __ldg(&pr[lo]);
+            const uint32_t ce = en.x, op = ce & 15u;
+            if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(en.y + q - (ce >> 4)));
             else if (EX && insertions && op == 1u) {                                    // ins[] / ins_offset (src/mod.c:1122-1127)
-                const int32_t left = pos + (int32_t)cr[lo] - 1;
+                const int32_t left = pos + (int32_t)en.y - 1;
                 if (left < 0) continue;                                                 // Q11
                 ref_pos = (uint32_t)left; ins16 = (q - (ce >> 4) + 1u) & 0xffffu;       // make_key's uint16_t (src/mod.c:428)
             } else continue;                                                            // src/mod.c:1127
@@ -372,8 +408,11 @@ __device__ __noinline__ void s_block_finish(const DecodeParams &P, uint32_t aoff
         const uint32_t cnt_n = s_count_n(aoff, lane), last1 = n_calls > 0u ? S.carry_sum : 0u;
         bound = last1 > cnt_n ? last1 : cnt_n;
     }
-    while (Z.p_hi < Z.n_u4 && Z.cum < bound) s_append(P, aoff, jb, S.seq, A.G, Z, lane);
+    while (Z.p_hi < Z.n_u4 && Z.cum < bound) s_append(P, aoff, jb, S.seq, A.G, A.bar, Z, lane);
     s_retire(P, aoff, jb, Z.p_ret, Z.p_hi, bound, lane);
+    __syncwarp();
+    if (lane == 0) *A.Z = Z;                                       // (a chunk may still be in flight: the next s_open_block drains it)
+    __syncwarp();
 }
 
 // MINB = resident CTAs per SM the register allocation is bounded for (8: 64 registers).
@@ -389,9 +428,9 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
         __syncthreads();
     }
     w_sparse_open(A.T, lane);
+    if (lane == 0) { mmc_mbar_init(A.bar, 1u); A.Z->pf_on = 0u; A.Z->pf_ph = 0u; }
+    __syncwarp();
     WRead *R = A.R;
-    uint32_t *flex = A.flex;
-    const uint32_t flex_words = (W.arena_bytes - (uint32_t)sizeof(SFixed)) / 4u;
     WState &S = R->st;
     for (;;) {
         uint32_t r = 0;
@@ -408,14 +447,7 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
             const uint32_t words = (uint32_t)((sizeof(WState) + sizeof(uint32_t) * (kWBlocks + 4) + sizeof(WBlock) * nb) / 4);
             for (uint32_t i = lane; i < words; i += 32u) dst[i] = src[i];
             __syncwarp();
-            if (S.n_stage <= flex_words) {                          // short CIGARs (HiFi): the prefix arrays move into the arena
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(S.flex_home);
-                uint4 *d4 = reinterpret_cast<uint4 *>(flex);
-                for (uint32_t i = lane; i < ((S.n_stage + 3u) >> 2); i += 32u) d4[i] = s4[i];
-                __syncwarp();
-                if (lane == 0) S.flex = flex;
-            }                                                      // else: looked up where k_flat_setup left them (HBM, L1-cached)
-            __syncwarp();
+            __syncwarp();                                          // (the CIGAR table stays where k_flat_setup wrote it: HBM, read through L1)
         }
         // ---- blocks in order
         const uint32_t n_blocks = S.n_blocks;
@@ -425,8 +457,7 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
             const WBlock *bd = &R->blk[jb];
             const uint32_t a0 = bd->hdr_end, a1 = bd->end;
             const uint32_t tail = !w_fast_ok(P, S, bd) ? 4u : (bd->cls == 0u ? 1u : 0u) + (ex ? 2u : 0u);
-            if (lane == 0) { s_stream_open(*A.Z, S, bd); S.carry_sum = 0; }
-            __syncwarp();
+            s_open_block(aoff, jb, lane);
             uint32_t carry_cnt = 0;
             for (uint32_t tb = a0 & ~15u; tb < a1; tb += (uint32_t)kWChunks * 16u) {
                 carry_cnt += s_tile(P, aoff, jb, tb, carry_cnt, ml_base, lane, tail);
@@ -443,7 +474,12 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
         }
         if (err) w_report(P, S.r, err, lane);
     }
-    w_sparse_close(P, s_arena(W.head_bytes + (threadIdx.x >> 5) * W.arena_bytes).T, lane);
+    {                                                              // no bulk copy may be in flight when the CTA retires
+        const SArena E = s_arena(W.head_bytes + (threadIdx.x >> 5) * W.arena_bytes);
+        SStream Z = *E.Z;
+        s_prefetch_wait(E.bar, Z);
+        w_sparse_close(P, E.T, lane);
+    }
 }
 
 }  // namespace mmc

@@ -80,6 +80,8 @@ struct WState {                              // warp-uniform state of the read b
     uint32_t carry_sum, prev_last;           // fused path: carries between the text tiles of a block
     uint32_t err;
     uint32_t n_semi, n_blocks;
+    uint32_t pairs;                          // stream layout: dir (32-base buckets) | uint2 {cq, cr} per op, in HBM (w_setup_read, stream mode)
+    uint32_t pad_;
 };
 
 struct WRead {                               // per read: shared memory (fused path) or global scratch (flat path)
@@ -227,6 +229,19 @@ __device__ __forceinline__ AlnHit w_cigar_lookup(const WState &S, const uint32_t
     AlnHit h; h.aln = -1; h.ins = -1; h.insoff = 0;
     const uint32_t total_q = S.total_q;
     if (q >= total_q) return h;
+    if (S.pairs) {                                               // stream layout, looked up in HBM (L1-cached)
+        const uint2 *pr = reinterpret_cast<const uint2 *>(flex + S.o_cq);
+        const uint32_t g = S.gshift, b = q >> g;
+        uint32_t lo = ldg32(flex + S.o_dir + b);
+        uint32_t hi = (((b + 1u) << g) < total_q) ? ldg32(flex + S.o_dir + b + 1u) : S.n_samp - 1u;
+        const uint32_t qlim = (q + 1u) << 4;
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (ldg32(&pr[mid].x) < qlim) lo = mid; else hi = mid - 1u; }
+        const uint2 e = __ldg(&pr[lo]);
+        const uint32_t op = e.x & 15u, d = q - (e.x >> 4);
+        if (op == 0u || op == 7u || op == 8u) h.aln = S.pos + (int32_t)(e.y + d);
+        else if (op == 1u) { h.ins = S.pos + (int32_t)e.y - 1; h.insoff = d + 1u; }
+        return h;
+    }
     const uint32_t *dir = flex + S.o_dir, *cq = flex + S.o_cq;
     const uint32_t g = S.gshift, b = q >> g;
     uint32_t lo = dir[b];
@@ -609,10 +624,10 @@ __device__ __forceinline__ bool w_needs_bitmap(const WBlock *bd) { return bd->an
 //   local_words  capacity of THIS arena for dir|cq|cr (k_flat_setup's arenas are smaller than the consumer's)
 template <bool TILE>
 __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, uint32_t flex_words, uint32_t local_words,
-                                          uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane, uint32_t stream = 0u) {
+                                          uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane, const FlatAlloc *stream = nullptr) {
     const WArena A = w_arena<TILE>(aoff);
     WRead *R = A.R;
-    uint32_t *flex = A.flex;
+    uint32_t *flex = A.flex;                                                         // (stream mode: re-pointed at the read's slice of the pool below)
     WState &S = R->st;
     const int32_t tid = P.tid[r];
     const uint32_t L = P.l_seq[r], n_cig = P.n_cigar[r], mm_len = P.mm_len[r];
@@ -628,7 +643,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
         S.ref2 = cd.ref2; S.excm = cd.excm; S.cells = cd.cells; S.ref_len = cd.len;
         S.r = r; S.L = L; S.n_cig = n_cig; S.mm_len = mm_len; S.ml_len = P.ml_len[r];
         S.rev = (P.flag[r] >> 4) & 1u; S.hp = P.hp[r]; S.tid = tid; S.pos = pos;
-        S.err = 0; S.cur_cls = 0xffu; S.cur_blk = 0; S.n_blocks = 0;
+        S.err = 0; S.cur_cls = 0xffu; S.cur_blk = 0; S.n_blocks = 0; S.pairs = stream ? 1u : 0u; S.pad_ = 0;
     }
 
     // ---- MM blocks: positions of ';'
@@ -676,8 +691,8 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
 
     // ---- scratch layout
     const uint32_t n_u4 = (L + 31u) >> 5;
-    uint32_t gshift = 8;
-    while (((L >> gshift) + 2u) > 160u) ++gshift;
+    uint32_t gshift = stream ? 5u : 8u;                                              // stream: the table lives in HBM, fine buckets keep the search to a step
+    while (!stream && ((L >> gshift) + 2u) > 160u) ++gshift;
     const uint32_t n_dir = (L >> gshift) + 2u;
     const uint32_t n_rd = (L >> 6) + 2u;
     const uint32_t bm_words = ((L + 31u) >> 5) + 1u;
@@ -692,12 +707,20 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
         if (n_samp == 0u) n_samp = 1u;
         n_ent = (n_u4 + (1u << ishift) - 1u) >> ishift;
         need = a4(n_dir + 2u * n_samp) + n_idx * a4(n_ent + 2u + n_rd) + n_bm * a4(bm_words);   // 16-byte aligned pieces
-        if (need <= cap && a4(n_dir + 2u * n_samp) <= local_words) break;
-        if (cshift >= (uint32_t)kWMaxCShift && (stream || ishift >= (uint32_t)kWMaxIShift)) { w_defer(defer_list, defer_n, r, lane); return false; }
-        if (stream || (2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
+        if (stream || (need <= cap && a4(n_dir + 2u * n_samp) <= local_words)) break;   // stream: un-sampled, in the pool
+        if (cshift >= (uint32_t)kWMaxCShift && ishift >= (uint32_t)kWMaxIShift) { w_defer(defer_list, defer_n, r, lane); return false; }
+        if ((2u * n_samp >= n_ent && cshift < (uint32_t)kWMaxCShift) || ishift >= (uint32_t)kWMaxIShift) ++cshift;
         else ++ishift;
     }
-    const uint32_t o_dir = 0, o_cq = n_dir, o_cr = o_cq + n_samp, o_var = a4(o_cr + n_samp);
+    const uint32_t o_dir = 0, o_cq = stream ? a4(n_dir) : n_dir, o_cr = o_cq + n_samp, o_var = a4(o_cq + 2u * n_samp);
+    if (stream) {                                                                    // dir | {cq, cr} pairs are written straight into the pool
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(stream->cursor, (unsigned long long)o_var);
+        base = ((unsigned long long)__shfl_sync(kFull, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)base, 0);
+        if (base + o_var > stream->cap) { w_defer(defer_list, defer_n, r, lane); return false; }
+        flex = stream->pool + base;
+    }
+    uint2 *pairs = reinterpret_cast<uint2 *>(flex + o_cq);
     if (lane == 0) {
         S.flex = flex; S.flex_home = flex;
         S.o_dir = o_dir; S.o_cq = o_cq; S.o_cr = o_cr;
@@ -725,7 +748,7 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     uint32_t carry_q = 0, carry_r = 0, big = 0;
     const uint32_t cmask = (1u << cshift) - 1u;
     const uint32_t rem_ref = (pos >= 0 && (uint32_t)pos < ref_len) ? ref_len - (uint32_t)pos : 0u;   // reference bases from pos on
-    if (n_cig == 0u && lane == 0) { flex[o_cq] = 15u; flex[o_cr] = 0; }
+    if (n_cig == 0u && lane == 0) { if (stream) pairs[0] = make_uint2(15u, 0u); else { flex[o_cq] = 15u; flex[o_cr] = 0; } }
     uint32_t w_next = lane < n_cig ? ldg32(cig + lane) : 0u;
     for (uint32_t base = 0; base < n_cig; base += 32u) {
         const uint32_t i = base + lane, w = w_next;
@@ -750,7 +773,8 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
                 if ((alnop || (op == 1u && P.insertions)) && q0 + ql > L) w_raise(R, kErrCigarLen);
                 if (alnop && r0 + len > rem_ref) w_raise(R, kErrRefRange);           // pos + r0 + len - 1 >= ref_len, or pos < 0
             }
-            if ((i & cmask) == 0u) { flex[o_cq + (i >> cshift)] = ((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op; flex[o_cr + (i >> cshift)] = r0; }
+            if (stream) pairs[i] = make_uint2(((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op, r0);
+            else if ((i & cmask) == 0u) { flex[o_cq + (i >> cshift)] = ((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op; flex[o_cr + (i >> cshift)] = r0; }
             if (ql > 0u && q0 < L) {                              // directory: sample that holds each bucket's first base
                 const uint32_t qe = q0 + ql < L ? q0 + ql : L;
                 for (uint32_t b = (q0 + (1u << gshift) - 1u) >> gshift; (b << gshift) < qe; ++b) flex[o_dir + b] = i >> cshift;

@@ -33,11 +33,11 @@ def test_scratch_paths(emul_lib, monkeypatch, name):
 # the default), the self-contained warp-per-read kernel, and the general CTA-per-read kernel (what the
 # other two defer reads to).  MMC_WARP_ARENA shrinks the per-warp shared-memory arena so that CIGAR / index
 # sampling and deferral actually happen on the small fixtures.
-PATHS = [("warp", None), ("general", None), ("split", "4608"), ("warp", "4400")]       # ("split", default) is the test above
+PATHS = [("warp", None), ("general", None), ("split", "4608"), ("warp", "4400"), ("stream", None), ("split", None)]   # (default: per batch, by read shape)
 
 
 @pytest.mark.parametrize("path,arena", PATHS, ids=[f"{p}-{a or 'default'}" for p, a in PATHS])
-@pytest.mark.parametrize("name", ["test7.tsv", "test5a.tsv", "test17a.tsv"])
+@pytest.mark.parametrize("name", ["test7.tsv", "test5a.tsv", "test17a.tsv", "test16.tsv", "test5c.tsv"])
 def test_decode_paths_agree(emul_lib, monkeypatch, path, arena, name):
     monkeypatch.setenv("MMC_DECODE_PATH", path)
     if arena:

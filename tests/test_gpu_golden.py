@@ -67,13 +67,13 @@ def test_cuda_vs_reference_binary_live(cuda_lib, bam, args):
         assert sorted_lines(out) == sorted_lines(ref_out)
 
 
-PATHS = [("split", None, "3"), ("split", None, "4"), ("split", None, "2"), ("warp", None, "3"), ("general", None, "3"),
+PATHS = [("stream", None, "3"), ("split", None, "3"), ("split", None, "4"), ("split", None, "2"), ("warp", None, "3"), ("general", None, "3"),
          ("split", "4608", "3"), ("warp", "4400", "4")]
 
 
 @pytest.mark.parametrize("path,arena,occ", PATHS, ids=[f"{p}-{a or 'default'}-occ{o}" for p, a, o in PATHS])
 def test_cuda_decode_paths_agree(cuda_lib, monkeypatch, path, arena, occ):
-    """Split (default), warp-per-read and general kernels, arena sizes that force sampling / deferral."""
+    """Streaming, split, warp-per-read and general kernels, arena sizes that force sampling / deferral."""
     monkeypatch.setenv("MMC_DECODE_PATH", path)
     monkeypatch.setenv("MMC_WARP_OCC", occ)
     if arena:

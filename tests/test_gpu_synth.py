@@ -35,7 +35,7 @@ def test_synthetic_parity_cuda_scratch(cuda_lib, monkeypatch, small_smem):
     run_synth(cuda_lib, 4, 800000, 0.5, "freq")
 
 
-@pytest.mark.parametrize("path,arena", [("split", None), ("warp", None), ("split", "5120"), ("general", None)])
+@pytest.mark.parametrize("path,arena", [("stream", None), ("split", None), ("warp", None), ("split", "5120"), ("general", None)])
 @pytest.mark.parametrize("config,cov", [(2, 3.0), (3, 2.0), (6, 1.5), (4, 0.5)])
 def test_synthetic_parity_cuda_paths(cuda_lib, monkeypatch, path, arena, config, cov):
     """Every decode path against the oracle on every config shape (50 kb reads of config 4 are mostly deferred
