@@ -906,25 +906,21 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
     if (lane >= (uint32_t)kWChunks) st = 0;
     uint32_t em = cm | (ncm << 16);                               // token terminators: ',' or the block end
     if (a1 >= p0 && a1 - p0 < 32u) em |= 1u << (a1 - p0);
-    T->em[lane] = em;
-    const uint32_t n_tok = (uint32_t)__popc(st);
+    const uint32_t n_tok = (uint32_t)__popc(st);                  // <= 8: a token is a digit and its ','
     const uint32_t incl = warp_incl_scan(n_tok, lane);
     const uint32_t tile_cnt = __shfl_sync(kFull, incl, 31);
-    uint32_t slot = incl - n_tok;
-    const uint32_t base_off = lane * 16u;
-    while (st) {                                                  // byte offset of every token of this chunk
-        T->rank[slot++] = base_off + (uint32_t)__ffs((int)st) - 1u;
-        st &= st - 1u;
-    }
+    const uint32_t slot0 = incl - n_tok;
     __syncwarp();
+    // every lane parses the tokens that start in its chunk (SWAR decimal parse, src/mod.c:1066-1085) and keeps the running
+    // sum of their skip+1; one saturating warp scan of the lanes' sums then gives every token its base rank (src/mod.c:1098)
     const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(T->text);
-    uint32_t carry = carry_in, total = 0;
-    for (uint32_t c0 = 0; c0 < tile_cnt; c0 += 32u) {
-        const uint32_t c = c0 + lane;
-        uint32_t x = 0;
-        if (c < tile_cnt) {                                       // one token per lane: SWAR decimal parse
-            const uint32_t off = T->rank[c];
-            const uint32_t rest = T->em[off >> 4] >> ((off & 15u) + 1u);
+    uint32_t px[8], acc = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        if (st) {
+            const uint32_t o = (uint32_t)__ffs((int)st) - 1u;
+            st &= st - 1u;
+            const uint32_t rest = em >> (o + 1u), off = lane * 16u + o;
             uint32_t nd = rest ? (uint32_t)__ffs((int)rest) : 32u, val = 0, bad = 0;
             if (nd > 9u) { bad = 1; nd = 0; }                     // src/mod.c:1080-1085
             if (nd <= 4u) {
@@ -940,14 +936,18 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
                 val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
             }
             if (bad) { w_raise(R, kErrMMSkip); val = 0; }
-            x = val + 1u < kWMaxL ? val + 1u : kWMaxL;             // >= 2^26 is past any read this path takes; 32 of them fit 32 bits
+            acc += val + 1u < kWMaxL ? val + 1u : kWMaxL;         // >= 2^26 is past any read this path takes; 8 of them fit 32 bits
         }
-        const uint32_t si = warp_incl_scan(x, lane);
-        if (c < tile_cnt) T->rank[c] = sat_add(carry, si) - 1u;   // base_rank (src/mod.c:1098)
-        const uint32_t rt = __shfl_sync(kFull, si, 31);
-        carry = sat_add(carry, rt); total = sat_add(total, rt);
+        px[t] = acc;
     }
-    *sum_out = total;
+    const uint32_t li = warp_incl_scan_sat(acc, lane);
+    uint32_t excl = __shfl_up_sync(kFull, li, 1);
+    if (lane == 0) excl = 0;
+    const uint32_t b0 = sat_add(carry_in, excl);
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+        if ((uint32_t)t < n_tok) T->rank[slot0 + (uint32_t)t] = sat_add(b0, px[t]) - 1u;   // base_rank (src/mod.c:1098)
+    *sum_out = __shfl_sync(kFull, li, 31);
     __syncwarp();
     return tile_cnt;
 }
@@ -982,6 +982,10 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
     const WCode cd = bd->code[0];
     const uint32_t m = cd.ctx_mode == kCtxFast ? cd.ctx_len : 0u, pat2 = cd.pat2;
     const uint32_t m2 = (1u << (2u * m)) - 1u, m1 = (1u << m) - 1u;
+    // occurrences of the context that can cover the call: the one starting j bases into the window puts pattern base
+    // m-1-j on the call's position, and ref == read base (src/mod.c:1164) forces that base to be the block's class
+    uint32_t jmask = 0;
+    for (uint32_t j = 0; j < m; ++j) jmask |= (uint32_t)(((pat2 >> (2u * (m - 1u - j))) & 3u) == (C0 ? 0u : cls)) << j;
     const uint8_t *lut = s_lut + cd.ri * 256;
     const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
     const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
@@ -1052,14 +1056,15 @@ __device__ __forceinline__ void w_tile_calls_fast(const DecodeParams &P, WRead *
                 const uint32_t W = __funnelshift_r(ldg32(ref2 + wi), ldg32(ref2 + wi + 1u), (w0 & 15u) * 2u);
                 const uint32_t E = __funnelshift_r(ldg32(excm + ei), ldg32(excm + ei + 1u), w0 & 31u);
                 uint32_t hit = 0;
-                for (uint32_t j = 0; j < m; ++j) hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
-                if (!hit) continue;                                                 // src/mod.c:1162-1172
-                uint32_t rc = cls;                                                  // the read base, as a 2-bit code
+                for (uint32_t jm = jmask; jm; jm &= jm - 1u) {
+                    const uint32_t j = (uint32_t)__ffs((int)jm) - 1u;
+                    hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
+                }
+                if (!hit) continue;                                                 // src/mod.c:1162-1172; a hit implies ref base == class base
                 if (C0) {                                                           // class 0 = 'A' and every other nt16 letter
                     const uint32_t nib = (ldg8(seq + (q >> 1)) >> ((~q & 1u) << 2)) & 0xfu;
-                    rc = nib == 1u ? 0u : 5u;
+                    if (nib != 1u) continue;                                        // the read base is not literally 'A'
                 }
-                if (((W >> (2u * (m - 1u))) & 3u) != rc) continue;
             }
         }
         if (prob > 0xffu) { w_raise(R, kErrMLIndex); continue; }                    // src/mod.c:1174
