@@ -268,88 +268,21 @@ __device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff,
 //   C0  class A (bit 31 of the position: the read base is not literally 'A')
 //   EX  any of: --insertions, --haplotypes, sampled CIGAR (kept out of the lean instantiation)
 // ---------------------------------------------------------------------------------------
-// aln[q] / ins[q] of get_aln() (src/mod.c:776-881) from the table k_flat_setup left in HBM: dir gives, per 32 bases of the
-// read, the op that holds the bucket's first base, so the op of q is one of a few entries after it.  Four are fetched at
-// once (two dependent round trips per call instead of a binary search's chain); longer buckets finish with the search.
-struct SMap { uint32_t lo, hi, qlim; };
-__device__ __forceinline__ SMap s_map_dir(const uint32_t *dir, uint32_t q, uint32_t g, uint32_t total_q, uint32_t last_samp) {
-    SMap M;
-    const uint32_t b = q >> g;
-    M.lo = ldg32(dir + b);
-    M.hi = (((b + 1u) << g) < total_q) ? ldg32(dir + b + 1u) : last_samp;
-    M.qlim = (q + 1u) << 4;
-    return M;
-}
-__device__ __forceinline__ uint2 s_map_entry(const uint2 *pr, const SMap &M) {
-    const uint32_t i1 = M.lo + 1u < M.hi ? M.lo + 1u : M.hi, i2 = M.lo + 2u < M.hi ? M.lo + 2u : M.hi, i3 = M.lo + 3u < M.hi ? M.lo + 3u : M.hi;
-    const uint2 e0 = __ldg(pr + M.lo), e1 = __ldg(pr + i1), e2 = __ldg(pr + i2), e3 = __ldg(pr + i3);
-    uint2 en = e0;                                                 // largest entry with q0 <= q (entries ascend)
-    if (e1.x < M.qlim) en = e1;
-    if (e2.x < M.qlim) en = e2;
-    if (e3.x < M.qlim) en = e3;
-    if (M.hi > M.lo + 3u && e3.x < M.qlim) {                       // a bucket with more than four ops (rare)
-        uint32_t lo = M.lo + 3u, hi = M.hi;
-        while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (ldg32(&pr[mid].x) < M.qlim) lo = mid; else hi = mid - 1u; }
-        en = __ldg(pr + lo);
-    }
-    return en;
-}
-
 // ---------------------------------------------------------------------------------------
 // phase B of a text tile, common case: read positions T->rank[0..n) -> reference positions -> context -> threshold ->
-// dense cells.  `freq`, one requested code per block (K == 1), canonical base A/C/G/T (w_fast_ok).  Two passes over the
-// tile so that the loads of a pass are independent of each other and several calls are in flight per lane:
-//   map     q -> ref_pos (in place; bit 31 carried along), ins_offset into the (now free) text buffer
-//   update  ref_pos -> reference window + ML byte -> LUT -> red.global.add.u64 / sparse record
+// dense cells.  `freq`, one requested code per block (K == 1), canonical base A/C/G/T (w_fast_ok).
 //   C0  class A (bit 31 of the position: the read base is not literally 'A')
-//   EX  --insertions and / or --haplotypes (kept out of the lean instantiation)
+//   EX  any of: --insertions, --haplotypes, sampled CIGAR (kept out of the lean instantiation)
 // ---------------------------------------------------------------------------------------
 template <bool C0, bool EX>
 __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTile *T, const uint8_t *s_lut, const WBlock *bd,
                                             uint32_t n, uint32_t cidx0, uint32_t ml_base, uint32_t lane) {
     const WState &S = R->st;
-    const uint32_t rev = S.rev;
-    const uint32_t insertions = EX ? (uint32_t)P.insertions : 0u;
-    uint16_t *insv = reinterpret_cast<uint16_t *>(T->text);        // kWTokCap x u16 <= the text buffer (free once the ranks exist)
-    {   // ---- map
-        const uint32_t *flex = S.flex;
-        const uint32_t *dir = flex + S.o_dir;
-        const uint2 *pr = reinterpret_cast<const uint2 *>(flex + S.o_cq);
-        const uint32_t total_q = S.total_q, g = S.gshift, last_samp = S.n_samp - 1u;
-        const int32_t pos = S.pos;
-        for (uint32_t c = lane; c < n; c += 64u) {
-            const uint32_t c2 = c + 32u;
-            const uint32_t qa = T->rank[c], qb = c2 < n ? T->rank[c2] : kNoCall;
-            const bool va = qa != kNoCall && (qa & 0x7fffffffu) < total_q, vb = qb != kNoCall && (qb & 0x7fffffffu) < total_q;
-            SMap ma, mb;
-            ma.lo = ma.hi = ma.qlim = 0; mb = ma;
-            if (va) ma = s_map_dir(dir, qa & 0x7fffffffu, g, total_q, last_samp);
-            if (vb) mb = s_map_dir(dir, qb & 0x7fffffffu, g, total_q, last_samp);
-            uint2 ea = make_uint2(15u, 0u), eb = ea;
-            if (va) ea = s_map_entry(pr, ma);
-            if (vb) eb = s_map_entry(pr, mb);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t cc = h ? c2 : c, qq = h ? qb : qa;
-                const uint2 en = h ? eb : ea;
-                if (cc >= n) break;
-                const uint32_t q = qq & 0x7fffffffu, op = en.x & 15u;
-                uint32_t out = kNoCall, ins16 = 0;
-                if (h ? vb : va) {
-                    if (op == 0u || op == 7u || op == 8u) out = ((uint32_t)(pos + (int32_t)(en.y + q - (en.x >> 4)))) | (qq & 0x80000000u);
-                    else if (EX && insertions && op == 1u) {                            // ins[] / ins_offset (src/mod.c:1122-1127)
-                        const int32_t left = pos + (int32_t)en.y - 1;
-                        if (left >= 0) { out = (uint32_t)left | (qq & 0x80000000u); ins16 = (q - (en.x >> 4) + 1u) & 0xffffu; }   // Q11; make_key's uint16_t
-                    }
-                }
-                T->rank[cc] = out;
-                if (EX && insertions) insv[cc] = (uint16_t)ins16;
-            }
-        }
-    }
-    __syncwarp();
-    // ---- update
-    const uint32_t ml_len = S.ml_len, ref_len = S.ref_len;
+    const uint32_t *flex = S.flex;                                 // dir | {cq, cr}: where k_flat_setup wrote them (HBM, read through L1)
+    const uint32_t *dir = flex + S.o_dir;
+    const uint2 *pr = reinterpret_cast<const uint2 *>(flex + S.o_cq);
+    const uint32_t rev = S.rev, total_q = S.total_q, g = S.gshift, last_samp = S.n_samp - 1u, ml_len = S.ml_len, ref_len = S.ref_len;
+    const int32_t pos = S.pos;
     const uint8_t *ml = S.ml;
     const uint32_t *ref2 = S.ref2, *excm = S.excm;
     unsigned long long *cells = S.cells;
@@ -364,7 +297,7 @@ __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTi
     const uint8_t *lut = s_lut + cd.ri * 256;
     const uint32_t per_pos = 2u * (uint32_t)P.n_code_slots * (uint32_t)P.n_hap_slots;
     const uint32_t within = (rev * (uint32_t)P.n_code_slots + cd.outc) * (uint32_t)P.n_hap_slots;
-    const uint32_t hslot = EX && P.haplotypes ? S.hp + 1u : 0u;
+    const uint32_t hslot = EX && P.haplotypes ? S.hp + 1u : 0u, insertions = EX ? (uint32_t)P.insertions : 0u, cshift = EX ? S.cshift : 0u;
     const uint32_t nrec = EX && hslot ? 2u : 1u;
     const uint32_t ml0 = ml_base + cidx0;
     uint32_t sp_pos = 0, sp_meta = 0;                              // EX: a sparse record waiting for the next converged point
@@ -376,19 +309,37 @@ __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTi
             pending = false;
             if (c >= n) continue;
         }
-        const uint32_t rr = T->rank[c];
-        if (rr == kNoCall) continue;                                                    // src/mod.c:1127
-        const uint32_t ref_pos = rr & 0x7fffffffu;
-        const uint32_t ins16 = (EX && insertions) ? (uint32_t)insv[c] : 0u;
+        const uint32_t qq = T->rank[c];
+        if (qq == kNoCall) continue;
+        const uint32_t q = qq & 0x7fffffffu;
         const uint32_t mi = ml0 + c;
-        const uint32_t prob = mi < ml_len ? ldg8(ml + mi) : 0x100u;
+        const uint32_t prob = mi < ml_len ? ldg8(ml + mi) : 0x100u;                    // issued early
+        // ---- map: aln[q] (get_aln, src/mod.c:776-881)
+        uint32_t ref_pos, ins16 = 0;
+        if (EX && cshift != 0u) {                                                       // sampled CIGAR (long reads): generic lookup
+            const AlnHit h = w_cigar_lookup(S, flex, q);
+            if (h.aln >= 0) ref_pos = (uint32_t)h.aln;
+            else if (insertions && h.ins >= 0) { ref_pos = (uint32_t)h.ins; ins16 = h.insoff & 0xffffu; }
+            else continue;
+        } else {
+            if (q >= total_q) continue;
+            const uint32_t b = q >> g;
+            uint32_t lo = ldg32(dir + b), hi = (((b + 1u) << g) < total_q) ? ldg32(dir + b + 1u) : last_samp;
+            const uint32_t qlim = (q + 1u) << 4;
+            while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (ldg32(&pr[mid].x) < qlim) lo = mid; else hi = mid - 1u; }   // 32-base buckets: a step or none
+            const uint2 en = __ldg(&pr[lo]);
+            const uint32_t ce = en.x, op = ce & 15u;
+            if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(en.y + q - (ce >> 4)));
+            else if (EX && insertions && op == 1u) {                                    // ins[] / ins_offset (src/mod.c:1122-1127)
+                const int32_t left = pos + (int32_t)en.y - 1;
+                if (left < 0) continue;                                                 // Q11
+                ref_pos = (uint32_t)left; ins16 = (q - (ce >> 4) + 1u) & 0xffffu;       // make_key's uint16_t (src/mod.c:428)
+            } else continue;                                                            // src/mod.c:1127
+        }
         // ---- context + base test (src/mod.c:1162-1172)
         if (m) {
-            if (ref_pos + 1u < m || ref_pos + m > ref_len) {                            // contig edge: generic test (needs the read position: cold)
-                if (!in_context(P.contigs[S.tid], ref_pos, rev ? P.req[cd.ri].pat_rc : P.req[cd.ri].pat, P.req[cd.ri].ctx_len)) continue;
-                const uint32_t letter = ref_letter(P.contigs[S.tid], ref_pos);
-                const uint32_t want = C0 ? (uint32_t)'A' : cls == 1u ? (uint32_t)'C' : cls == 2u ? (uint32_t)'G' : (uint32_t)'T';
-                if (letter != want || (C0 && (rr >> 31))) continue;
+            if (ref_pos + 1u < m || ref_pos + m > ref_len) {                            // contig edge: generic test
+                if (!w_ctx_slow(P, S, (uint32_t)cd.ri, ref_pos, q, 0u)) continue;
             } else {
                 const uint32_t w0 = ref_pos + 1u - m, wi = w0 >> 4, ei = w0 >> 5;
                 const uint32_t W = __funnelshift_r(ldg32(ref2 + wi), ldg32(ref2 + wi + 1u), (w0 & 15u) * 2u);
@@ -399,7 +350,7 @@ __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTi
                     hit |= (uint32_t)((((W >> (2u * j)) & m2) == pat2) & (((E >> j) & m1) == 0u));
                 }
                 if (!hit) continue;                                                     // a hit implies ref base == class base
-                if (C0 && (rr >> 31)) continue;                                         // ... and the read base must be that letter
+                if (C0 && (qq >> 31)) continue;                                         // ... and the read base must be that letter
             }
         }
         if (prob > 0xffu) { w_raise(R, kErrMLIndex); continue; }                        // src/mod.c:1174
@@ -507,7 +458,7 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
         // ---- blocks in order
         const uint32_t n_blocks = S.n_blocks;
         uint32_t ml_base = 0, err = 0;
-        const bool ex = P.insertions || P.haplotypes;
+        const bool ex = P.insertions || P.haplotypes || S.cshift != 0u;
         for (uint32_t jb = 0; jb < n_blocks; ++jb) {
             const WBlock *bd = &R->blk[jb];
             const uint32_t a0 = bd->hdr_end, a1 = bd->end;

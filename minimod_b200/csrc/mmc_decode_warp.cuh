@@ -746,55 +746,89 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     const uint32_t cmask = (1u << cshift) - 1u;
     const uint32_t rem_ref = (pos >= 0 && (uint32_t)pos < ref_len) ? ref_len - (uint32_t)pos : 0u;   // reference bases from pos on
     if (n_cig == 0u && lane == 0) { if (stream) pairs[0] = make_uint2(15u, 0u); else { flex[o_cq] = 15u; flex[o_cr] = 0; } }
-    // 128 ops per step, four consecutive ops per lane (one 16-byte load): a serial prefix inside the lane, then ONE pair of
-    // warp scans over the lanes' sums.  Exact while every length is < 2^24 (128 x 2^24 = 2^31; the running totals saturate at
-    // kSat like sat_add); a read with a longer op is left to k_decode, whose block scans saturate at every step.
-    for (uint32_t base = 0; base < n_cig; base += 128u) {
-        const uint32_t i0 = base + lane * 4u;
-        uint4 w4 = make_uint4(0, 0, 0, 0);
-        if (i0 < n_cig) w4 = ld16(reinterpret_cast<const uint8_t *>(cig + i0));     // (the pool has 64 bytes of slack past the last slice)
-        const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        uint32_t opv[4], qlv[4], rlv[4], sq = 0, sr = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
+    if (!stream) {
+    // arena layout: 32 ops per step; the next step's words are loaded before this step's are used.  Plain warp scans are exact
+    // while every length is < 2^26 (32 x 2^26 = 2^31; the running totals saturate at kSat like sat_add); a read with a longer
+    // op is left to k_decode, whose block scans saturate at every step.
+        uint32_t w_next = lane < n_cig ? ldg32(cig + lane) : 0u;
+        for (uint32_t base = 0; base < n_cig; base += 32u) {
+            const uint32_t i = base + lane, w = w_next;
+            if (i + 32u < n_cig) w_next = ldg32(cig + i + 32u);
             uint32_t op = 15u, len = 0, ql = 0, rl = 0;
-            if (i0 + (uint32_t)k < n_cig) {
-                op = wv[k] & 15u; len = wv[k] >> 4;
+            if (i < n_cig) {
+                op = w & 15u; len = w >> 4;
                 if (op == 0u || op == 7u || op == 8u) { ql = len; rl = len; }
                 else if (op == 1u || op == 4u) ql = len;
                 else if (op == 2u || op == 3u) rl = len;
                 else if (op == 5u) w_raise(R, kErrHardClip);
                 else w_raise(R, kErrCigarOp);
             }
+            big |= len >> 26;
+            const uint32_t iq = warp_incl_scan(ql, lane), ir = warp_incl_scan(rl, lane);
+            if (i < n_cig) {
+                uint32_t q0 = carry_q + (iq - ql), r0 = carry_r + (ir - rl);
+                if (q0 > kSat) q0 = kSat;
+                if (r0 > kSat) r0 = kSat;
+                if (len > 0u) {
+                    const bool alnop = op == 0u || op == 7u || op == 8u;
+                    if ((alnop || (op == 1u && P.insertions)) && q0 + ql > L) w_raise(R, kErrCigarLen);
+                    if (alnop && r0 + len > rem_ref) w_raise(R, kErrRefRange);           // pos + r0 + len - 1 >= ref_len, or pos < 0
+                }
+                if ((i & cmask) == 0u) { flex[o_cq + (i >> cshift)] = ((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op; flex[o_cr + (i >> cshift)] = r0; }
+                if (ql > 0u && q0 < L) {                              // directory: sample that holds each bucket's first base
+                    const uint32_t qe = q0 + ql < L ? q0 + ql : L;
+                    for (uint32_t b = (q0 + (1u << gshift) - 1u) >> gshift; (b << gshift) < qe; ++b) flex[o_dir + b] = i >> cshift;
+                }
+            }
+            carry_q += __shfl_sync(kFull, iq, 31); if (carry_q > kSat) carry_q = kSat;
+            carry_r += __shfl_sync(kFull, ir, 31); if (carry_r > kSat) carry_r = kSat;
+        }
+    } else {
+    // stream layout (long CIGARs): 128 ops per step, four consecutive ops per lane (one 16-byte load), branch-free op tables,
+    // a serial prefix inside the lane and ONE pair of warp scans over the lanes' sums; the fatal conditions are collected
+    // as flags and raised after the loop.  Exact while every length is < 2^24 (128 x 2^24 = 2^31).
+    uint32_t bad = 0;                                                                // 1 hard clip, 2 unhandled op, 4 CIGAR past the read, 8 past the contig
+    const uint32_t insq = P.insertions ? 0x183u : 0x181u;                            // ops whose query range must lie inside the read: M = X (+ I)
+    for (uint32_t base = 0; base < n_cig; base += 128u) {
+        const uint32_t i0 = base + lane * 4u;
+        uint4 w4 = make_uint4(0, 0, 0, 0);
+        if (i0 < n_cig) w4 = ld16(reinterpret_cast<const uint8_t *>(cig + i0));     // (the pool has 64 bytes of slack past the last slice)
+        const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        uint32_t qlv[4], rlv[4], sq = 0, sr = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t valid = i0 + (uint32_t)k < n_cig ? 1u : 0u, op = wv[k] & 15u, len = valid ? wv[k] >> 4 : 0u;
+            const uint32_t ql = len & (0u - ((0x193u >> op) & 1u)), rl = len & (0u - ((0x18du >> op) & 1u));   // M I S = X / M D N = X
+            bad |= valid & (op == 5u ? 1u : 0u);
+            bad |= (valid & (((0x19fu | 0x20u) >> op) & 1u ^ 1u)) << 1;
             big |= len >> 24;
-            opv[k] = op; qlv[k] = ql; rlv[k] = rl; sq += ql; sr += rl;
+            qlv[k] = ql; rlv[k] = rl; sq += ql; sr += rl;
         }
         if (__ballot_sync(kFull, big != 0u)) break;                                  // (deferred below)
         const uint32_t iq = warp_incl_scan(sq, lane), ir = warp_incl_scan(sr, lane);
         uint32_t q0 = carry_q + (iq - sq), r0 = carry_r + (ir - sr);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t i = i0 + (uint32_t)k, op = opv[k], ql = qlv[k], rl = rlv[k];
+            const uint32_t i = i0 + (uint32_t)k, op = wv[k] & 15u, ql = qlv[k], rl = rlv[k];
             if (q0 > kSat) q0 = kSat;
             if (r0 > kSat) r0 = kSat;
             if (i < n_cig) {
-                const uint32_t len = ql | rl;
-                if (len > 0u) {
-                    const bool alnop = op == 0u || op == 7u || op == 8u;
-                    if ((alnop || (op == 1u && P.insertions)) && q0 + ql > L) w_raise(R, kErrCigarLen);
-                    if (alnop && r0 + len > rem_ref) w_raise(R, kErrRefRange);       // pos + r0 + len - 1 >= ref_len, or pos < 0
-                }
-                if (stream) pairs[i] = make_uint2(((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op, r0);
-                else if ((i & cmask) == 0u) { flex[o_cq + (i >> cshift)] = ((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op; flex[o_cr + (i >> cshift)] = r0; }
-                if (ql > 0u && q0 < L) {                          // directory: sample that holds each bucket's first base
-                    const uint32_t qe = q0 + ql < L ? q0 + ql : L;
-                    for (uint32_t b = (q0 + (1u << gshift) - 1u) >> gshift; (b << gshift) < qe; ++b) flex[o_dir + b] = i >> cshift;
+                bad |= ((ql > 0u && ((insq >> op) & 1u) && q0 + ql > L) ? 4u : 0u) | ((rl > 0u && ((0x181u >> op) & 1u) && r0 + rl > rem_ref) ? 8u : 0u);
+                pairs[i] = make_uint2(((q0 < kWMaxL ? q0 : kWMaxL) << 4) | op, r0);
+                const uint32_t qe = q0 + ql < L ? q0 + ql : L;                    // directory: op that holds each bucket's first base
+                uint32_t b = (q0 + 31u) >> 5;
+                if (ql > 0u && (b << 5) < qe) {
+                    flex[o_dir + b] = i;
+                    for (++b; (b << 5) < qe; ++b) flex[o_dir + b] = i;
                 }
             }
             q0 += ql; r0 += rl;
         }
         carry_q += __shfl_sync(kFull, iq, 31); if (carry_q > kSat) carry_q = kSat;
         carry_r += __shfl_sync(kFull, ir, 31); if (carry_r > kSat) carry_r = kSat;
+    }
+    const uint32_t allbad = __ballot_sync(kFull, bad & 1u) ? 1u : __ballot_sync(kFull, bad & 2u) ? 2u : __ballot_sync(kFull, bad & 4u) ? 4u : __ballot_sync(kFull, bad & 8u) ? 8u : 0u;
+    if (allbad) w_raise(R, allbad == 1u ? kErrHardClip : allbad == 2u ? kErrCigarOp : allbad == 4u ? kErrCigarLen : kErrRefRange);
     }
     if (__ballot_sync(kFull, big != 0u)) { w_defer(defer_list, defer_n, r, lane); return false; }
     if (lane == 0) S.total_q = carry_q < L ? carry_q : L;
@@ -919,43 +953,48 @@ __device__ __forceinline__ uint32_t w_tile_ranks(WRead *R, WTile *T, uint32_t tb
     if (lane >= (uint32_t)kWChunks) st = 0;
     uint32_t em = cm | (ncm << 16);                               // token terminators: ',' or the block end
     if (a1 >= p0 && a1 - p0 < 32u) em |= 1u << (a1 - p0);
-    const uint32_t n_tok = (uint32_t)__popc(st);                  // <= 8: a token is a digit and its ','
+    T->em[lane] = em;
+    const uint32_t n_tok = (uint32_t)__popc(st);
     const uint32_t incl = warp_incl_scan(n_tok, lane);
     const uint32_t tile_cnt = __shfl_sync(kFull, incl, 31);
-    const uint32_t slot0 = incl - n_tok;
-    __syncwarp();
-    // every lane parses the tokens that start in its chunk (SWAR decimal parse, src/mod.c:1066-1085) and keeps the running
-    // sum of their skip+1; one saturating warp scan of the lanes' sums then gives every token its base rank (src/mod.c:1098)
-    const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(T->text);
-    uint32_t acc = 0, slot = slot0;
-    while (st) {                                                  // (kept a loop: the instruction caches are small)
-        const uint32_t o = (uint32_t)__ffs((int)st) - 1u;
+    uint32_t slot = incl - n_tok;
+    const uint32_t base_off = lane * 16u;
+    while (st) {                                                  // byte offset of every token of this chunk
+        T->rank[slot++] = base_off + (uint32_t)__ffs((int)st) - 1u;
         st &= st - 1u;
-        const uint32_t rest = em >> (o + 1u), off = lane * 16u + o;
-        uint32_t nd = rest ? (uint32_t)__ffs((int)rest) : 32u, val = 0, bad = 0;
-        if (nd > 9u) { bad = 1; nd = 0; }                         // src/mod.c:1080-1085
-        if (nd <= 4u) {
-            const uint32_t w0 = tx32[off >> 2], w1 = tx32[(off >> 2) + 1u];
-            uint32_t dg = __funnelshift_r(w0, w1, (off & 3u) * 8u) - 0x30303030u;
-            const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
-            bad |= (((dg + 0x76767676u) | dg) & 0x80808080u & keep) != 0u;
-            dg = (dg & keep) << ((8u * (4u - nd)) & 31u);
-            if (nd == 0u) dg = 0;
-            const uint32_t pr = (dg * 10u + (dg >> 8)) & 0x00ff00ffu;                  // (10*b0+b1) | (10*b2+b3) << 16
-            val = (pr & 0xffffu) * 100u + (pr >> 16);
-        } else {
-            val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
-        }
-        if (bad) { w_raise(R, kErrMMSkip); val = 0; }
-        acc += val + 1u < kWMaxL ? val + 1u : kWMaxL;             // >= 2^26 is past any read this path takes; 8 of them fit 32 bits
-        T->rank[slot++] = acc;                                    // the lane's running sum; the warp's part is added below
     }
-    const uint32_t li = warp_incl_scan_sat(acc, lane);
-    uint32_t excl = __shfl_up_sync(kFull, li, 1);
-    if (lane == 0) excl = 0;
-    const uint32_t b0 = sat_add(carry_in, excl);
-    for (uint32_t t = slot0; t < slot; ++t) T->rank[t] = sat_add(b0, T->rank[t]) - 1u;   // base_rank (src/mod.c:1098)
-    *sum_out = __shfl_sync(kFull, li, 31);
+    __syncwarp();
+    const uint32_t *tx32 = reinterpret_cast<const uint32_t *>(T->text);
+    uint32_t carry = carry_in, total = 0;
+    for (uint32_t c0 = 0; c0 < tile_cnt; c0 += 32u) {
+        const uint32_t c = c0 + lane;
+        uint32_t x = 0;
+        if (c < tile_cnt) {                                       // one token per lane: SWAR decimal parse
+            const uint32_t off = T->rank[c];
+            const uint32_t rest = T->em[off >> 4] >> ((off & 15u) + 1u);
+            uint32_t nd = rest ? (uint32_t)__ffs((int)rest) : 32u, val = 0, bad = 0;
+            if (nd > 9u) { bad = 1; nd = 0; }                     // src/mod.c:1080-1085
+            if (nd <= 4u) {
+                const uint32_t w0 = tx32[off >> 2], w1 = tx32[(off >> 2) + 1u];
+                uint32_t dg = __funnelshift_r(w0, w1, (off & 3u) * 8u) - 0x30303030u;
+                const uint32_t keep = nd >= 4u ? 0xffffffffu : ((1u << (8u * nd)) - 1u);
+                bad |= (((dg + 0x76767676u) | dg) & 0x80808080u & keep) != 0u;
+                dg = (dg & keep) << ((8u * (4u - nd)) & 31u);
+                if (nd == 0u) dg = 0;
+                const uint32_t pr = (dg * 10u + (dg >> 8)) & 0x00ff00ffu;              // (10*b0+b1) | (10*b2+b3) << 16
+                val = (pr & 0xffffu) * 100u + (pr >> 16);
+            } else {
+                val = w_parse_long(reinterpret_cast<const uint8_t *>(T->text) + off, nd, &bad);
+            }
+            if (bad) { w_raise(R, kErrMMSkip); val = 0; }
+            x = val + 1u < kWMaxL ? val + 1u : kWMaxL;             // >= 2^26 is past any read this path takes; 32 of them fit 32 bits
+        }
+        const uint32_t si = warp_incl_scan(x, lane);
+        if (c < tile_cnt) T->rank[c] = sat_add(carry, si) - 1u;   // base_rank (src/mod.c:1098)
+        const uint32_t rt = __shfl_sync(kFull, si, 31);
+        carry = sat_add(carry, rt); total = sat_add(total, rt);
+    }
+    *sum_out = total;
     __syncwarp();
     return tile_cnt;
 }
