@@ -442,31 +442,15 @@ def region_halo(env, tid=0):
     torch, dist, lib = env.torch, env.dist, env.lib
 
     def run(ctx):
-        lo, hi = C.c_uint32(), C.c_uint32()
-        env.chk(ctx, lib.mmc_touched_range(ctx, tid, C.byref(lo), C.byref(hi)))
-        mine = torch.tensor([int(lo.value), int(hi.value)], dtype=torch.int64, device="cuda")
-        allr = [torch.zeros_like(mine) for _ in range(env.world)]
-        dist.all_gather(allr, mine)
-        spans = [(int(t[0]), int(t[1])) for t in allr]         # [lo, hi) every rank's reads touched
+        stats = {}
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nbytes, width = 0, 0
         torch.cuda.synchronize()
         ev0.record()
-        for k in range(env.world - 1):                          # boundary k | k+1: first position rank k+1's reads touch
-            s = spans[k + 1][0]
-            e = max(sp[1] for sp in spans[:k + 1])              # how far the reads of the ranks left of it ran
-            if e <= s:
-                continue
-            assert e <= spans[k + 1][1] or k + 1 == env.world - 1 or e <= spans[k + 2][0], "halo wider than a slice"
-            cells = shard.dense_tensor(lib, ctx, tid, s, e, cuda=True)
-            dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-            nbytes += cells.numel() * 8; width = max(width, e - s)
-            if env.rank != k + 1:                               # the slice owner prints these positions; the others drop them
-                cells.zero_()
+        width = shard.exchange_halos(lib, ctx, tid, None, env.rank, dist, cuda=True, stats=stats)   # bounds: from each rank's first read
         ev1.record()
         torch.cuda.synchronize()
-        return {"allreduce_ms": ev0.elapsed_time(ev1), "bytes": int(nbytes), "max_halo_positions": int(width),
-                "collective": "ncclAllReduce(sum, int64 view of the n_called|n_mod cells) per boundary, over NVLink"}
+        return {"allreduce_ms": ev0.elapsed_time(ev1), "bytes": int(stats.get("bytes", 0)), "max_halo_positions": int(width),
+                "collective": "ncclAllReduce(sum, int64 view of the n_called|n_mod cells) per boundary, over NVLink (minimod_b200.shard.exchange_halos)"}
     return run
 
 

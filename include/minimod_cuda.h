@@ -242,6 +242,16 @@ int  mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end);
 /* [lo,hi) of contig tid that any submitted read (or mmc_dense_touch) has covered so far; lo>=hi: nothing */
 int  mmc_touched_range(mmc_ctx *ctx, int32_t tid, uint32_t *lo, uint32_t *hi);
 
+/* ---- multi-GPU in ONE process (the reference is one process, src/freq_main.c:404-474): ctxs[0..n) -- one context per
+ *      device, created over the same contig table -- hold the reads that START in consecutive slices of contig tid
+ *      (context k: positions p with p*n/len == k).  A read may run past its slice, so its counts sit in its own context's
+ *      copy of the next slices' cells.  This call sums those boundary cells across the contexts -- ncclAllReduce(sum,
+ *      uint64) over NVLink when the contexts are on different devices (libnccl.so.2, loaded on demand), a device-local
+ *      add when they share one -- leaves every position's total with the context that owns it and zeroes the other
+ *      copies, so that the union of the contexts' mmc_freq_finalize() rows is the single-device table (sparse rows of a
+ *      boundary stay where they were counted: add rows with equal keys).  ms / bytes (optional): device time and volume. */
+int  mmc_region_reduce(mmc_ctx *const *ctxs, int32_t n_ctx, int32_t tid, double *ms, uint64_t *bytes);
+
 int  mmc_get_timers(mmc_ctx *ctx, mmc_timers_t *out);
 int  mmc_reset_timers(mmc_ctx *ctx);
 /* one line naming the kernels the decode stage of this context launches (measurement reports) */

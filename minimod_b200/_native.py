@@ -87,7 +87,7 @@ CUDA_SYMBOLS = [
     "mmc_create", "mmc_destroy", "mmc_strerror", "mmc_abi_version", "mmc_ref_add", "mmc_ref_commit",
     "mmc_batch_acquire", "mmc_batch_submit", "mmc_batch_wait", "mmc_batch_release", "mmc_batch_upload",
     "mmc_batch_launch", "mmc_sync", "mmc_freq_finalize", "mmc_freq_reset", "mmc_code_name", "mmc_view_fetch",
-    "mmc_dense_slice", "mmc_dense_touch", "mmc_touched_range", "mmc_get_timers", "mmc_reset_timers", "mmc_last_decode_ms", "mmc_describe",
+    "mmc_dense_slice", "mmc_dense_touch", "mmc_touched_range", "mmc_get_timers", "mmc_reset_timers", "mmc_last_decode_ms", "mmc_describe", "mmc_region_reduce",
 ]
 
 
@@ -119,6 +119,7 @@ def _declare_cuda(lib):
         "mmc_reset_timers": (C.c_int, [vp]),
         "mmc_last_decode_ms": (C.c_int, [vp, P(MmcBatch), P(C.c_double)]),
         "mmc_describe": (C.c_char_p, [vp]),
+        "mmc_region_reduce": (C.c_int, [P(vp), i32, i32, P(C.c_double), P(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -13,6 +13,9 @@
 #include <algorithm>
 #include <string>
 #include <chrono>
+#ifndef MMC_EMUL
+#include <dlfcn.h>
+#endif
 #include <vector>
 
 #include "../../include/minimod_cuda.h"
@@ -118,6 +121,7 @@ struct mmc_ctx {
     // finalize scratch, grown on demand and kept: tile counts / offsets / totals, device rows, pinned host rows
     uint32_t *d_tile_count = nullptr; unsigned long long *d_tile_off = nullptr, *d_totals = nullptr;
     size_t fin_tiles_cap = 0, fin_jobs_cap = 0;
+    uint32_t *d_fin_mask = nullptr;                                  // one bit per scanned cell (+ 1 word: n_called overflow flag)
     FreqRecDev *d_rows = nullptr; size_t d_rows_cap = 0;
     // device-side finalize of the sparse side buffer (mmc_sparse.cuh): grow-only scratch
     uint64_t sparse_dev_min = 1u << 16;                              // fewer records than this: host sort (a few ms at most)
@@ -146,6 +150,9 @@ int fail(mmc_ctx *ctx, int code, const char *fmt, ...) {
     if (ctx) ctx->err = buf; else g_create_error = buf;
     return code;
 }
+
+// several contexts (one per device) may live in one process: every entry point makes its context's device current
+#define MMC_DEV(ctx) do { if (ctx) cudaSetDevice((ctx)->opts.device); } while (0)
 
 #define CU(ctx, call)                                                                           \
     do {                                                                                        \
@@ -744,6 +751,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
 }
 
 void mmc_destroy(mmc_ctx *ctx) {
+    MMC_DEV(ctx);
     if (!ctx) return;
     cudaDeviceSynchronize();
     for (Slot &s : ctx->slots) {
@@ -782,6 +790,7 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (ctx->d_exc_n) cudaFree(ctx->d_exc_n);
     if (ctx->d_tile_count) cudaFree(ctx->d_tile_count);
     if (ctx->d_tile_off) cudaFree(ctx->d_tile_off);
+    if (ctx->d_fin_mask) cudaFree(ctx->d_fin_mask);
     if (ctx->d_totals) cudaFree(ctx->d_totals);
     if (ctx->d_rows) cudaFree(ctx->d_rows);
     if (ctx->d_sp_scratch) cudaFree(ctx->d_sp_scratch);
@@ -800,6 +809,7 @@ void mmc_destroy(mmc_ctx *ctx) {
 }
 
 int mmc_ref_add(mmc_ctx *ctx, int32_t tid, const char *seq, uint32_t len) {
+    MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
     if (tid < 0 || (size_t)tid >= ctx->contigs.size()) return fail(ctx, MMC_EINVAL, "mmc_ref_add: tid %d out of range", tid);
     ContigHost &c = ctx->contigs[tid];
@@ -877,6 +887,7 @@ int mmc_ref_add(mmc_ctx *ctx, int32_t tid, const char *seq, uint32_t len) {
 }
 
 int mmc_ref_commit(mmc_ctx *ctx) {
+    MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
     std::vector<ContigDev> tab(ctx->contigs.size());
     for (size_t i = 0; i < tab.size(); ++i) {
@@ -889,6 +900,7 @@ int mmc_ref_commit(mmc_ctx *ctx) {
 }
 
 int mmc_batch_acquire(mmc_ctx *ctx, mmc_batch_t **batch) {
+    MMC_DEV(ctx);
     if (!ctx || !batch) return MMC_EINVAL;
     Slot *pick = nullptr;
     for (Slot &s : ctx->slots) if (!s.acquired) { pick = &s; break; }
@@ -903,6 +915,7 @@ int mmc_batch_acquire(mmc_ctx *ctx, mmc_batch_t **batch) {
 }
 
 int mmc_batch_upload(mmc_ctx *ctx, mmc_batch_t *batch) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s || !s->acquired) return fail(ctx, MMC_ESTATE, "mmc_batch_upload: not an acquired batch");
     if (!ctx->committed) return fail(ctx, MMC_ESTATE, "mmc_batch_upload: call mmc_ref_commit() first");
@@ -918,6 +931,7 @@ int mmc_batch_upload(mmc_ctx *ctx, mmc_batch_t *batch) {
 }
 
 int mmc_batch_launch(mmc_ctx *ctx, mmc_batch_t *batch) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s || !s->acquired || !s->uploaded) return fail(ctx, MMC_ESTATE, "mmc_batch_launch: batch was not uploaded");
     int rc = wait_slot(ctx, *s);
@@ -926,6 +940,7 @@ int mmc_batch_launch(mmc_ctx *ctx, mmc_batch_t *batch) {
 }
 
 int mmc_batch_submit(mmc_ctx *ctx, mmc_batch_t *batch) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s || !s->acquired) return fail(ctx, MMC_ESTATE, "mmc_batch_submit: not an acquired batch");
     if (!ctx->committed) return fail(ctx, MMC_ESTATE, "mmc_batch_submit: call mmc_ref_commit() first");
@@ -937,12 +952,14 @@ int mmc_batch_submit(mmc_ctx *ctx, mmc_batch_t *batch) {
 }
 
 int mmc_batch_wait(mmc_ctx *ctx, mmc_batch_t *batch) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s) return fail(ctx, MMC_ESTATE, "mmc_batch_wait: unknown batch");
     return wait_slot(ctx, *s);
 }
 
 int mmc_batch_release(mmc_ctx *ctx, mmc_batch_t *batch) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s) return fail(ctx, MMC_ESTATE, "mmc_batch_release: unknown batch");
     int rc = wait_slot(ctx, *s);
@@ -951,6 +968,7 @@ int mmc_batch_release(mmc_ctx *ctx, mmc_batch_t *batch) {
 }
 
 int mmc_sync(mmc_ctx *ctx) {
+    MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
     int first = MMC_OK;
     for (Slot &s : ctx->slots) { int rc = wait_slot(ctx, s); if (rc != MMC_OK && first == MMC_OK) first = rc; }
@@ -958,6 +976,7 @@ int mmc_sync(mmc_ctx *ctx) {
 }
 
 int mmc_last_decode_ms(mmc_ctx *ctx, mmc_batch_t *batch, double *ms) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s || !ms) return MMC_EINVAL;
     int rc = wait_slot(ctx, *s);
@@ -1075,6 +1094,7 @@ static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn) {
 extern "C" {
 
 int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
+    MMC_DEV(ctx);
     if (!ctx || !recs || !n_recs) return MMC_EINVAL;
     if (ctx->opts.subtool != MMC_FREQ) return fail(ctx, MMC_ESTATE, "mmc_freq_finalize: context was created for view");
     int rc = mmc_sync(ctx);
@@ -1131,8 +1151,11 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             if (ctx->d_tile_count) cudaFree(ctx->d_tile_count);
             if (ctx->d_tile_off) cudaFree(ctx->d_tile_off);
             ctx->d_tile_count = nullptr; ctx->d_tile_off = nullptr; ctx->fin_tiles_cap = 0;
+            if (ctx->d_fin_mask) cudaFree(ctx->d_fin_mask);
+            ctx->d_fin_mask = nullptr;
             CU(ctx, cudaMalloc((void **)&ctx->d_tile_count, 4 * tiles));
             CU(ctx, cudaMalloc((void **)&ctx->d_tile_off, 8 * tiles));
+            CU(ctx, cudaMalloc((void **)&ctx->d_fin_mask, 4 * (tiles * (kTileCells / 32) + 1)));
             ctx->fin_tiles_cap = tiles;
         }
         if (jobs.size() > ctx->fin_jobs_cap) {
@@ -1143,6 +1166,8 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             CU(ctx, cudaMallocHost((void **)&ctx->h_totals, 8 * jobs.size()));
             ctx->fin_jobs_cap = jobs.size();
         }
+        uint32_t *d_overflow = ctx->d_fin_mask + ctx->fin_tiles_cap * (kTileCells / 32);
+        CU(ctx, cudaMemsetAsync(d_overflow, 0, 4, ctx->fin_stream));
         std::vector<FinalizeParams> fps(jobs.size());
         for (size_t k = 0; k < jobs.size(); ++k) {
             const Job &j = jobs[k];
@@ -1152,6 +1177,7 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             fp.n_cells = j.n_cells; fp.tid = j.tid; fp.lo = j.lo;
             fp.n_code_slots = ctx->n_code_slots; fp.n_hap_slots = ctx->n_hap_slots; fp.haplotypes = ctx->opts.haplotypes;
             fp.tile_count = ctx->d_tile_count + j.tile0; fp.tile_offset = ctx->d_tile_off + j.tile0; fp.cells_per_tile = kTileCells;
+            fp.mask = ctx->d_fin_mask + j.tile0 * (kTileCells / 32); fp.overflow = d_overflow;
             MMC_LAUNCH(k_count_nonzero, (unsigned)j.n_tiles, 256u, ctx->fin_stream, fp);
             CU(ctx, cudaGetLastError());
             MMC_LAUNCH(k_scan_tiles, 1u, 256u, ctx->fin_stream, fp.tile_count, fp.tile_offset, (uint32_t)j.n_tiles, ctx->d_totals + k);
@@ -1159,7 +1185,11 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             ctx->tm.kernel_launches += 2;
         }
         CU(ctx, cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 8 * jobs.size(), cudaMemcpyDeviceToHost, ctx->fin_stream));
+        uint32_t h_overflow = 0;
+        CU(ctx, cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->fin_stream));
         CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+        if (h_overflow)                                       // src/mod.c:899-901,922-924: the reference aborts too
+            return fail(ctx, MMC_ENOMEM, "n_called overflowed for a position (more than 4294967295 calls on one cell). Please report this issue.");
         uint64_t total = 0;
         for (size_t k = 0; k < jobs.size(); ++k) total += ctx->h_totals[k];
         if (total) {
@@ -1295,6 +1325,7 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
 }
 
 int mmc_freq_reset(mmc_ctx *ctx) {
+    MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
     int rc = mmc_sync(ctx);
     if (rc != MMC_OK) return rc;
@@ -1317,6 +1348,7 @@ int mmc_freq_reset(mmc_ctx *ctx) {
 }
 
 int mmc_view_fetch(mmc_ctx *ctx, mmc_batch_t *batch, const mmc_view_rec_t **recs, uint64_t *n_recs) {
+    MMC_DEV(ctx);
     Slot *s = ctx ? slot_of(ctx, batch) : nullptr;
     if (!s || !recs || !n_recs) return MMC_EINVAL;
     if (ctx->opts.subtool != MMC_VIEW) return fail(ctx, MMC_ESTATE, "mmc_view_fetch: context was created for freq");
@@ -1367,6 +1399,7 @@ int mmc_dense_slice(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end, voi
 }
 
 int mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end) {
+    MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
     if (tid < 0 || (size_t)tid >= ctx->contigs.size() || !ctx->contigs[tid].loaded) return fail(ctx, MMC_EINVAL, "mmc_dense_touch: bad contig %d", tid);
     if (start >= end || end > ctx->contigs[tid].len) return fail(ctx, MMC_EINVAL, "mmc_dense_touch: bad range");
@@ -1382,7 +1415,113 @@ int mmc_dense_touch(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end) {
     return MMC_OK;
 }
 
+// cells of a boundary region: dst += src (contexts that share a device), and the clearing of the non-owners' copies
+__global__ void k_cells_add(unsigned long long *dst, const unsigned long long *src, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+int mmc_region_reduce(mmc_ctx *const *ctxs, int32_t n_ctx, int32_t tid, double *ms_out, uint64_t *bytes_out) {
+    if (ms_out) *ms_out = 0;
+    if (bytes_out) *bytes_out = 0;
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return MMC_EINVAL;
+    mmc_ctx *c0 = ctxs[0];
+    if (n_ctx == 1) return MMC_OK;
+    if (tid < 0 || (size_t)tid >= c0->contigs.size()) return fail(c0, MMC_EINVAL, "mmc_region_reduce: bad contig %d", tid);
+    const uint64_t len = c0->contigs[tid].len;
+    std::vector<uint32_t> lo(n_ctx), hi(n_ctx);
+    bool same_device = true;
+    for (int k = 0; k < n_ctx; ++k) {
+        mmc_ctx *c = ctxs[k];
+        if (!c || c->opts.subtool != MMC_FREQ || c->contigs.size() != c0->contigs.size() || !c->contigs[tid].loaded || !c->contigs[tid].dev.cells ||
+            c->n_code_slots != c0->n_code_slots || c->n_hap_slots != c0->n_hap_slots)
+            return fail(c0, MMC_EINVAL, "mmc_region_reduce: context %d does not hold dense counts of contig %d with the same layout", k, tid);
+        CU(c0, cudaSetDevice(c->opts.device));
+        int rc = mmc_touched_range(c, tid, &lo[k], &hi[k]);
+        if (rc != MMC_OK) { c0->err = c->err; return rc; }
+        if (c->opts.device != c0->opts.device) same_device = false;
+    }
+    const size_t spp = 2 * (size_t)c0->n_code_slots * c0->n_hap_slots;
+    auto slice_start = [&](int k) -> uint64_t { return ((uint64_t)k * len + (uint64_t)n_ctx - 1) / (uint64_t)n_ctx; };   // first p with p*n/len == k
+    struct Region { int owner; uint32_t s, e; };
+    std::vector<Region> regions;
+    uint32_t reach = 0;                                       // how far the reads of the contexts left of the boundary ran
+    for (int j = 1; j < n_ctx; ++j) {
+        if (hi[j - 1] > lo[j - 1]) reach = std::max(reach, hi[j - 1]);
+        const uint64_t s = slice_start(j), e = std::min<uint64_t>(std::min<uint64_t>(j + 1 < n_ctx ? slice_start(j + 1) : len, reach), len);
+        if (e > s) regions.push_back({j, (uint32_t)s, (uint32_t)e});
+    }
+    if (regions.empty()) return MMC_OK;
+#ifndef MMC_EMUL
+    typedef struct ncclComm *comm_t;
+    typedef int (*init_all_t)(comm_t *, int, const int *);
+    typedef int (*allreduce_t)(const void *, void *, size_t, int, int, comm_t, cudaStream_t);
+    typedef int (*void_t)(void);
+    typedef int (*destroy_t)(comm_t);
+    typedef const char *(*errstr_t)(int);
+    void *h = nullptr;
+    init_all_t p_init = nullptr; allreduce_t p_ar = nullptr; void_t p_gs = nullptr, p_ge = nullptr; destroy_t p_destroy = nullptr; errstr_t p_err = nullptr;
+    std::vector<comm_t> comms(n_ctx, nullptr);
+    if (!same_device) {
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return fail(c0, MMC_ECUDA, "mmc_region_reduce: contexts on several devices need NCCL, but libnccl.so.2 cannot be loaded (%s)", dlerror());
+        p_init = (init_all_t)dlsym(h, "ncclCommInitAll"); p_ar = (allreduce_t)dlsym(h, "ncclAllReduce");
+        p_gs = (void_t)dlsym(h, "ncclGroupStart"); p_ge = (void_t)dlsym(h, "ncclGroupEnd");
+        p_destroy = (destroy_t)dlsym(h, "ncclCommDestroy"); p_err = (errstr_t)dlsym(h, "ncclGetErrorString");
+        if (!p_init || !p_ar || !p_gs || !p_ge || !p_destroy) return fail(c0, MMC_ECUDA, "mmc_region_reduce: libnccl.so.2 lacks the expected symbols");
+        std::vector<int> devs(n_ctx);
+        for (int k = 0; k < n_ctx; ++k) devs[k] = ctxs[k]->opts.device;
+        const int rc = p_init(comms.data(), n_ctx, devs.data());
+        if (rc != 0) return fail(c0, MMC_ECUDA, "ncclCommInitAll failed: %s", p_err ? p_err(rc) : "?");
+    }
+#endif
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t bytes = 0;
+    for (const Region &R : regions) {
+        const size_t n_cells = (size_t)(R.e - R.s) * spp;
+        bytes += n_cells * 8;
+        if (same_device) {
+            mmc_ctx *own = ctxs[R.owner];
+            for (int k = 0; k < n_ctx; ++k) {
+                if (k == R.owner) continue;
+                const unsigned grid = (unsigned)std::min<size_t>((n_cells + 255) / 256, (size_t)own->sm_count * 16);
+                MMC_LAUNCH(k_cells_add, grid, 256u, own->fin_stream, own->contigs[tid].dev.cells + (size_t)R.s * spp,
+                           (const unsigned long long *)(ctxs[k]->contigs[tid].dev.cells + (size_t)R.s * spp), (unsigned long long)n_cells);
+                CU(c0, cudaGetLastError());
+            }
+            CU(c0, cudaStreamSynchronize(own->fin_stream));
+        }
+#ifndef MMC_EMUL
+        else {
+            int rc = p_gs();
+            for (int k = 0; k < n_ctx && rc == 0; ++k) {
+                unsigned long long *cells = ctxs[k]->contigs[tid].dev.cells + (size_t)R.s * spp;
+                rc = p_ar(cells, cells, n_cells, 5 /* ncclUint64: n_called and n_mod never carry into each other */, 0 /* ncclSum */, comms[k], ctxs[k]->fin_stream);
+            }
+            const int rc2 = p_ge();
+            if (rc != 0 || rc2 != 0) return fail(c0, MMC_ECUDA, "ncclAllReduce failed: %s", p_err ? p_err(rc ? rc : rc2) : "?");
+            for (int k = 0; k < n_ctx; ++k) { CU(c0, cudaSetDevice(ctxs[k]->opts.device)); CU(c0, cudaStreamSynchronize(ctxs[k]->fin_stream)); }
+        }
+#endif
+        for (int k = 0; k < n_ctx; ++k) {                    // the owner keeps the sums, every other copy is cleared
+            mmc_ctx *c = ctxs[k];
+            CU(c0, cudaSetDevice(c->opts.device));
+            if (k == R.owner) { int rc = mmc_dense_touch(c, tid, R.s, R.e); if (rc != MMC_OK) { c0->err = c->err; return rc; } }
+            else CU(c0, cudaMemsetAsync(c->contigs[tid].dev.cells + (size_t)R.s * spp, 0, n_cells * 8, c->fin_stream));
+        }
+        for (int k = 0; k < n_ctx; ++k) { CU(c0, cudaSetDevice(ctxs[k]->opts.device)); CU(c0, cudaStreamSynchronize(ctxs[k]->fin_stream)); }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+#ifndef MMC_EMUL
+    if (!same_device) { for (comm_t cm : comms) if (cm) p_destroy(cm); }
+#endif
+    if (ms_out) *ms_out = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (bytes_out) *bytes_out = bytes;
+    CU(c0, cudaSetDevice(c0->opts.device));
+    return MMC_OK;
+}
+
 int mmc_touched_range(mmc_ctx *ctx, int32_t tid, uint32_t *lo, uint32_t *hi) {
+    MMC_DEV(ctx);
     if (!ctx || !lo || !hi) return MMC_EINVAL;
     if (tid < 0 || (size_t)tid >= ctx->contigs.size()) return fail(ctx, MMC_EINVAL, "mmc_touched_range: bad contig %d", tid);
     int rc = mmc_sync(ctx);

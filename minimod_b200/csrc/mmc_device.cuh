@@ -958,18 +958,46 @@ struct FinalizeParams {
     uint32_t cells_per_tile;
     void *out;                         // mmc_freq_rec_t[]
     unsigned long long out_base;
+    uint32_t *mask;                    // one bit per cell of the range: non-zero (written by k_count_nonzero, read by k_emit_records)
+    uint32_t *overflow;                // set when a cell shows n_mod > n_called: n_called wrapped (src/mod.c:899-901)
 };
 
-__global__ void k_count_nonzero(FinalizeParams p) {
-    __shared__ uint32_t ws[32];
+// Pass 1 of the compaction: the only full read of the dense range.  One CTA (8 warps) per tile; every warp owns a contiguous
+// eighth of the tile and leaves one ballot word per 32 cells, so that pass 2 never touches an empty cell again.
+__global__ void __launch_bounds__(256) k_count_nonzero(FinalizeParams p) {
+    __shared__ uint32_t ws[8];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned long long c0 = (unsigned long long)blockIdx.x * p.cells_per_tile;
     unsigned long long c1 = c0 + p.cells_per_tile;
     if (c1 > p.n_cells) c1 = p.n_cells;
-    uint32_t n = 0;
-    for (unsigned long long c = c0 + threadIdx.x; c < c1; c += blockDim.x) n += p.cells[c] != 0ull;
-    uint32_t e = n, d = 0, tot, td;
-    block_scan2_sat(e, d, tot, td, ws);
-    if (threadIdx.x == 0) p.tile_count[blockIdx.x] = tot;
+    const uint32_t per_warp = p.cells_per_tile / 8u;
+    unsigned long long w0 = c0 + (unsigned long long)warp * per_warp, w1 = w0 + per_warp;
+    if (w0 > c1) w0 = c1;
+    if (w1 > c1) w1 = c1;
+    uint32_t cnt = 0, myword = 0, bad = 0;
+    const uint32_t n_words = (uint32_t)((w1 - w0 + 31u) >> 5);
+    for (uint32_t w = 0; w < n_words; w += 2u) {                  // two loads in flight per lane
+        const unsigned long long ca = w0 + (unsigned long long)w * 32u + lane, cb = ca + 32u;
+        const unsigned long long va = ca < w1 ? p.cells[ca] : 0ull, vb = cb < w1 ? p.cells[cb] : 0ull;
+        const uint32_t fa = __ballot_sync(0xffffffffu, va != 0ull), fb = __ballot_sync(0xffffffffu, vb != 0ull);
+        bad |= (uint32_t)((uint32_t)(va >> 32) > (uint32_t)va) | (uint32_t)((uint32_t)(vb >> 32) > (uint32_t)vb);
+        if (lane == (w & 31u)) myword = fa;
+        if (lane == ((w + 1u) & 31u)) myword = fb;
+        cnt += (uint32_t)__popc(fa) + (uint32_t)__popc(fb);
+        if (((w + 2u) & 31u) == 0u || w + 2u >= n_words) {          // 32 words collected (or the slice ends): one coalesced store
+            const uint32_t first = w & ~31u, mine = first + lane;
+            if (mine < n_words) p.mask[(w0 >> 5) + mine] = myword;
+            myword = 0;
+        }
+    }
+    if (__ballot_sync(0xffffffffu, bad != 0u) && lane == 0) atomicOr(p.overflow, 1u);
+    if (lane == 0) ws[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; ++w) tot += ws[w];
+        p.tile_count[blockIdx.x] = tot;
+    }
 }
 
 // single-CTA exclusive scan of tile counts
@@ -999,10 +1027,9 @@ struct FreqRecDev {                    // == mmc_freq_rec_t
     uint16_t reserved;
 };
 
-// One CTA (8 warps) per tile, one barrier per tile: every warp owns a contiguous eighth of the tile, counts its
-// non-zero cells (ballots over 64 cells per step), the warp totals are prefix-summed through shared memory, and each
-// warp then re-reads its slice (L1/L2-hot) and writes its rows in cell order.  Empty tiles -- most of a genome at
-// CpG density -- leave after one load of the tile's count.
+// Pass 2: one CTA (8 warps) per non-empty tile, one barrier per tile.  Every warp owns a contiguous eighth of the tile; it
+// reads the ballot words pass 1 left (32 words = 1024 cells per load), the warp totals are prefix-summed through shared
+// memory, and only the non-zero cells are fetched again and written as rows in cell order.
 __global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
     __shared__ uint32_t ws[8];
     if (p.tile_count[blockIdx.x] == 0u) return;
@@ -1014,11 +1041,14 @@ __global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
     unsigned long long w0 = c0 + (unsigned long long)warp * per_warp, w1 = w0 + per_warp;
     if (w0 > c1) w0 = c1;
     if (w1 > c1) w1 = c1;
+    const uint32_t n_words = (uint32_t)((w1 - w0 + 31u) >> 5);
     uint32_t cnt = 0;
-    for (unsigned long long cb = w0; cb < w1; cb += 64u) {
-        const unsigned long long c = cb + lane;
-        const unsigned long long v0 = c < w1 ? p.cells[c] : 0ull, v1 = c + 32u < w1 ? p.cells[c + 32u] : 0ull;
-        cnt += (uint32_t)__popc(__ballot_sync(0xffffffffu, v0 != 0ull)) + (uint32_t)__popc(__ballot_sync(0xffffffffu, v1 != 0ull));
+    for (uint32_t wb = 0; wb < n_words; wb += 32u) {
+        const uint32_t m = wb + lane < n_words ? p.mask[(w0 >> 5) + wb + lane] : 0u;
+        uint32_t c = (uint32_t)__popc(m);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        cnt += c;
     }
     if (lane == 0) ws[warp] = cnt;
     __syncthreads();
@@ -1027,29 +1057,31 @@ __global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
     for (uint32_t w = 0; w < warp; ++w) running += ws[w];
     FreqRecDev *out = reinterpret_cast<FreqRecDev *>(p.out) + p.out_base + p.tile_offset[blockIdx.x];
     const uint32_t spp = 2u * (uint32_t)p.n_code_slots * (uint32_t)p.n_hap_slots;   // slots per position
-    for (unsigned long long cb = w0; cb < w1; cb += 64u) {
-        const unsigned long long c = cb + lane;
-        const unsigned long long v0 = c < w1 ? p.cells[c] : 0ull, v1 = c + 32u < w1 ? p.cells[c + 32u] : 0ull;
-        const uint32_t f0 = __ballot_sync(0xffffffffu, v0 != 0ull), f1 = __ballot_sync(0xffffffffu, v1 != 0ull);
-        if (!(f0 | f1)) continue;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const unsigned long long v = half ? v1 : v0, cc = half ? c + 32u : c;
-            if (v == 0ull) continue;
-            const uint32_t at = running + (half ? (uint32_t)__popc(f0) + (uint32_t)__popc(f1 & lt) : (uint32_t)__popc(f0 & lt));
-            const unsigned long long posi = cc / spp;
-            uint32_t slot = (uint32_t)(cc - posi * spp);
-            const uint32_t hslot = slot % (uint32_t)p.n_hap_slots; slot /= (uint32_t)p.n_hap_slots;
-            const uint32_t code = slot % (uint32_t)p.n_code_slots; slot /= (uint32_t)p.n_code_slots;
-            FreqRecDev rec;
-            rec.tid = p.tid; rec.pos = p.lo + (int32_t)posi;
-            rec.n_called = (uint32_t)v; rec.n_mod = (uint32_t)(v >> 32);
-            rec.ins_offset = 0;
-            rec.hap = p.haplotypes ? (int16_t)((int32_t)hslot - 1) : (int16_t)-1;
-            rec.strand = (uint8_t)slot; rec.code = (uint8_t)code; rec.reserved = 0;
-            out[at] = rec;
+    for (uint32_t wb = 0; wb < n_words; wb += 32u) {
+        const uint32_t mword = wb + lane < n_words ? p.mask[(w0 >> 5) + wb + lane] : 0u;
+        uint32_t todo = __ballot_sync(0xffffffffu, mword != 0u);                  // words of this group with any non-zero cell
+        while (todo) {
+            const uint32_t wi = (uint32_t)__ffs((int)todo) - 1u;
+            todo &= todo - 1u;
+            const uint32_t f = __shfl_sync(0xffffffffu, mword, (int)wi);
+            if ((f >> lane) & 1u) {
+                const unsigned long long cc = w0 + (unsigned long long)(wb + wi) * 32u + lane;
+                const unsigned long long v = p.cells[cc];
+                const uint32_t at = running + (uint32_t)__popc(f & lt);
+                const unsigned long long posi = cc / spp;
+                uint32_t slot = (uint32_t)(cc - posi * spp);
+                const uint32_t hslot = slot % (uint32_t)p.n_hap_slots; slot /= (uint32_t)p.n_hap_slots;
+                const uint32_t code = slot % (uint32_t)p.n_code_slots; slot /= (uint32_t)p.n_code_slots;
+                FreqRecDev rec;
+                rec.tid = p.tid; rec.pos = p.lo + (int32_t)posi;
+                rec.n_called = (uint32_t)v; rec.n_mod = (uint32_t)(v >> 32);
+                rec.ins_offset = 0;
+                rec.hap = p.haplotypes ? (int16_t)((int32_t)hslot - 1) : (int16_t)-1;
+                rec.strand = (uint8_t)slot; rec.code = (uint8_t)code; rec.reserved = 0;
+                out[at] = rec;
+            }
+            running += (uint32_t)__popc(f);
         }
-        running += (uint32_t)__popc(f0) + (uint32_t)__popc(f1);
     }
 }
 

@@ -193,6 +193,34 @@ bool BamFile::open(const std::string &path, std::string *err, int threads) {
     return true;
 }
 
+static size_t aux_size(const uint8_t *s, const uint8_t *end);
+
+// BAM's n_cigar field has 16 bits; a CIGAR with more ops (ultra-long ONT reads) is stored as the placeholder
+// <l_seq>S<ref_len>N with the real ops in a CG:B,I tag (SAM spec 4.2.2).  htslib puts them back when it reads the
+// record (bam_tag2cigar() in sam_read1()), so the reference sees the real CIGAR: do the same, and drop the tag.
+static void restore_long_cigar(BamRecord *r) {
+    if (r->n_cigar == 0 || r->tid < 0 || r->pos < 0) return;
+    uint32_t c0; memcpy(&c0, r->cigar(), 4);
+    if ((c0 & 15u) != 4u || (c0 >> 4) != (uint32_t)r->l_qseq) return;
+    const uint8_t *cg = r->aux_get("CG");
+    if (!cg || cg[0] != 'B' || cg[1] != 'I') return;
+    uint32_t n; memcpy(&n, cg + 2, 4);
+    if (n < r->n_cigar || n >= (1u << 29)) return;
+    const uint8_t *tag0 = cg - 2, *tag1 = cg + 6 + 4 * (size_t)n, *end = r->end();
+    if (tag1 > end) return;
+    std::vector<uint8_t> d;
+    d.reserve((size_t)r->l_data + 4 * (size_t)n + 8);
+    const uint8_t *base = r->data.data();
+    d.insert(d.end(), base, r->cigar());                                  // qname
+    d.insert(d.end(), cg + 6, cg + 6 + 4 * (size_t)n);                    // the real ops
+    d.insert(d.end(), r->seq(), tag0);                                    // seq, qual, aux before CG
+    d.insert(d.end(), tag1, end);                                         // aux after CG
+    r->n_cigar = n;
+    r->l_data = (int32_t)d.size();
+    d.resize(d.size() + 8, 0);
+    r->data.swap(d);
+}
+
 int BamFile::next(BamRecord *r) {
     uint8_t b4[4], fx[32];
     long got = read_some(b4, 4);
@@ -210,6 +238,7 @@ int BamFile::next(BamRecord *r) {
     memset(r->data.data() + r->l_data, 0, 8);
     size_t fixed = (size_t)r->l_qname + 4 * (size_t)r->n_cigar + ((size_t)(r->l_qseq < 0 ? 0 : r->l_qseq) + 1) / 2 + (size_t)(r->l_qseq < 0 ? 0 : r->l_qseq);
     if (r->l_qseq < 0 || fixed > (size_t)r->l_data) return -1;
+    restore_long_cigar(r);
     return 1;
 }
 

@@ -13,6 +13,8 @@
 #include <sys/time.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -66,6 +68,9 @@ struct Opt {
     int bedmethyl = 0, insertions = 0, haplotypes = 0, allow_secondary = 0, alt_alleles = 0, skip_supplementary = 0;
     int progress_interval = 0;
     int device = 0;
+    std::vector<int> devices;                     // --devices: one context per entry, batches dealt by contig owner (or region)
+    int shard_regions = 0;                        // --shard-regions: split the longest contig by read start, halo counts reduced at the end
+    int64_t sparse_cap = 0;                       // --sparse-cap
     const char *mod_codes = nullptr;
     std::string mod_threshes;
     const char *output_file = nullptr;
@@ -93,6 +98,9 @@ static void print_help(FILE *fp, const Opt &o, const char *tool) {
     fprintf(fp, "\nadvanced options:\n");
     fprintf(fp, "   --debug-break INT          break after processing the specified no. of batches\n");
     fprintf(fp, "   --device INT               CUDA device ordinal [%d]\n", o.device);
+    fprintf(fp, "   --devices LIST             comma separated CUDA devices (e.g. 0,1,2,3): contigs are dealt to them by length (LPT)\n");
+    fprintf(fp, "   --shard-regions            with --devices: split the longest contig by read start; boundary counts are summed with NCCL\n");
+    fprintf(fp, "   --sparse-cap INT[K/M/G]    initial records of the side buffer for counts without a dense cell (it grows) [auto]\n");
 }
 
 static int run_tool(int subtool, int argc, char *argv[]) {
@@ -109,6 +117,8 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         {"insertions", no_argument, 0, 1001},      {"haplotypes", no_argument, 0, 1002},
         {"allow-secondary", no_argument, 0, 1003}, {"include-non-ref", no_argument, 0, 1004},
         {"skip-supplementary", no_argument, 0, 1005}, {"device", required_argument, 0, 1006},
+        {"devices", required_argument, 0, 1007},   {"shard-regions", no_argument, 0, 1008},
+        {"sparse-cap", required_argument, 0, 1009},
         {0, 0, 0, 0}};
     const char *optstring = subtool == MMC_FREQ ? "m:c:t:B:K:v:p:o:hVb" : "c:t:B:K:v:p:o:hV";
 
@@ -146,6 +156,10 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         else if (c == 1004) opt.alt_alleles = 1;
         else if (c == 1005) opt.skip_supplementary = 1;
         else if (c == 1006) opt.device = atoi(optarg);
+        else if (c == 1007) {
+            for (const char *q = optarg; *q;) { opt.devices.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+        } else if (c == 1008) opt.shard_regions = 1;
+        else if (c == 1009) opt.sparse_cap = mm_parse_num(optarg);
         else { print_help(fp_help, opt, tool); exit(fp_help == stdout ? EXIT_SUCCESS : EXIT_FAILURE); }
     }
 
@@ -188,19 +202,49 @@ static int run_tool(int subtool, int argc, char *argv[]) {
     std::vector<const char *> names;
     for (const std::string &n : bam.names) names.push_back(n.c_str());
 
-    mmc_opts_t mo;
-    memset(&mo, 0, sizeof(mo));
-    mo.struct_size = sizeof(mo);
-    mo.subtool = subtool; mo.n_mods = (int32_t)mmods.size(); mo.mods = mmods.data();
-    mo.insertions = opt.insertions; mo.haplotypes = opt.haplotypes; mo.device = opt.device;
-    mo.n_slots = 3; mo.max_reads = (uint64_t)opt.batch_size; mo.max_bytes = (uint64_t)opt.batch_size_bases;
-    mo.seq_packing = 2;                          // SEQ crosses PCIe at 2 bits per base + exceptions
-    mmc_ctx *ctx = nullptr;
-    if (mmc_create(&ctx, &mo, (int32_t)names.size(), names.data(), bam.lens.data()) != MMC_OK) {
-        ERROR("%s", mmc_strerror(nullptr)); exit(EXIT_FAILURE);
+    if (opt.devices.empty()) opt.devices.push_back(opt.device);
+    const int ndev = (int)opt.devices.size();
+    // ---- who owns what: contigs are dealt to the devices by longest-processing-time bin packing; with
+    // --shard-regions the longest contig is instead cut into ndev slices by read start and every device keeps a full copy of it
+    const int n_contigs = (int)bam.names.size();
+    std::vector<int> owner(n_contigs, 0);
+    int big_tid = -1;
+    if (ndev > 1) {
+        std::vector<int> order(n_contigs);
+        for (int i = 0; i < n_contigs; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return bam.lens[a] != bam.lens[b] ? bam.lens[a] > bam.lens[b] : a < b; });
+        if (opt.shard_regions && n_contigs > 0) big_tid = order[0];
+        std::vector<uint64_t> load(ndev, 0);
+        for (int tid : order) {
+            if (tid == big_tid) continue;
+            int d = 0;
+            for (int k = 1; k < ndev; ++k) if (load[k] < load[d]) d = k;
+            owner[tid] = d; load[d] += bam.lens[tid];
+        }
     }
+    auto owner_of = [&](int32_t tid, int32_t pos) -> int {
+        if (tid < 0 || tid >= n_contigs) return -1;
+        if (tid == big_tid) { int64_t d = (int64_t)(pos < 0 ? 0 : pos) * ndev / std::max<uint32_t>(1u, bam.lens[tid]); return (int)std::min<int64_t>(d, ndev - 1); }
+        return owner[tid];
+    };
 
-    // ---- reference: FASTA parsing on the host, packing + context evaluation on the device
+    std::vector<mmc_ctx *> ctxs(ndev, nullptr);
+    for (int d = 0; d < ndev; ++d) {
+        mmc_opts_t mo;
+        memset(&mo, 0, sizeof(mo));
+        mo.struct_size = sizeof(mo);
+        mo.subtool = subtool; mo.n_mods = (int32_t)mmods.size(); mo.mods = mmods.data();
+        mo.insertions = opt.insertions; mo.haplotypes = opt.haplotypes; mo.device = opt.devices[d];
+        mo.n_slots = 3; mo.max_reads = (uint64_t)opt.batch_size; mo.max_bytes = (uint64_t)opt.batch_size_bases;
+        mo.sparse_capacity = (uint64_t)opt.sparse_cap;
+        mo.seq_packing = 2;                          // SEQ crosses PCIe at 2 bits per base + exceptions
+        if (mmc_create(&ctxs[d], &mo, (int32_t)names.size(), names.data(), bam.lens.data()) != MMC_OK) {
+            ERROR("%s", mmc_strerror(nullptr)); exit(EXIT_FAILURE);
+        }
+    }
+    mmc_ctx *ctx = ctxs[0];
+
+    // ---- reference: FASTA parsing on the host, packing + context evaluation on the device that owns the contig
     double realtime1 = realtime();
     fprintf(stderr, "[%s] Loading reference genome %s\n", func, ref_file);
     {
@@ -213,12 +257,19 @@ static int run_tool(int subtool, int argc, char *argv[]) {
             int32_t tid = -1;
             for (size_t i = 0; i < bam.names.size(); ++i) if (bam.names[i] == r.name) { tid = (int32_t)i; break; }
             if (tid < 0) continue;                       // contigs the BAM header does not know can never be hit
-            if (mmc_ref_add(ctx, tid, r.seq.data(), (uint32_t)r.seq.size()) != MMC_OK) {
-                // a length mismatch is only fatal in the reference when a read maps there (src/mod.c:861)
-                WARNING("%s", mmc_strerror(ctx));
+            for (int d = 0; d < ndev; ++d) {
+                if (tid != big_tid && owner[tid] != d) continue;
+                const int rc = mmc_ref_add(ctxs[d], tid, r.seq.data(), (uint32_t)r.seq.size());
+                if (rc == MMC_EINVAL && r.seq.size() != bam.lens[tid]) {
+                    // a length mismatch is only fatal in the reference when a read maps there (src/mod.c:861)
+                    WARNING("%s", mmc_strerror(ctxs[d]));
+                } else if (rc != MMC_OK) {               // out of device memory, CUDA failure: nothing sensible can follow
+                    ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE);
+                }
             }
         }
-        if (mmc_ref_commit(ctx) != MMC_OK) { ERROR("%s", mmc_strerror(ctx)); exit(EXIT_FAILURE); }
+        for (int d = 0; d < ndev; ++d)
+            if (mmc_ref_commit(ctxs[d]) != MMC_OK) { ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE); }
         fprintf(stderr, "[%s] Reference contexts loaded in %.3f sec\n", func, realtime() - realtime2);
     }
 
@@ -228,48 +279,73 @@ static int run_tool(int subtool, int argc, char *argv[]) {
     LoadOpts lo;
     lo.batch_size = opt.batch_size; lo.batch_size_bases = opt.batch_size_bases;
     lo.allow_secondary = opt.allow_secondary; lo.skip_supplementary = opt.skip_supplementary;
-    lo.keep_qnames = subtool == MMC_VIEW;
+    lo.keep_qnames = 1;                               // read names: view rows, and the reference's per-read fatal messages
     BatchLoader loader(&bam, lo);
+    if (ndev > 1) loader.set_owner([&](const BamRecord &r) { return (r.flag & 4) ? -1 : owner_of(r.tid, r.pos); });
 
     uint64_t total_reads = 0, total_bytes = 0, processed_reads = 0, processed_bytes = 0;
     double load_time = 0, output_time = 0;
     int32_t counter = 0;
     const int n_slots = 3;
-    std::vector<mmc_batch_t *> ring(n_slots, nullptr);
-    std::vector<BatchMeta> metas(n_slots);
-    auto code_names = [&]() {
+    struct Ring { std::vector<mmc_batch_t *> b; std::vector<BatchMeta> meta; int next = 0; };
+    std::vector<Ring> rings(ndev);
+    for (Ring &r : rings) { r.b.assign(n_slots, nullptr); r.meta.resize(n_slots); }
+    auto code_names_of = [&](mmc_ctx *c) {
         std::vector<std::string> v(256);
-        for (int i = 0; i < 256; ++i) v[i] = mmc_code_name(ctx, i);
+        for (int i = 0; i < 256; ++i) v[i] = mmc_code_name(c, i);
         return v;
     };
-    auto die_read = [&](mmc_batch_t *b, const BatchMeta &meta) {
-        (void)b; (void)meta;
-        ERROR("%s", mmc_strerror(ctx));
+    // a per-read fatal condition: the library names the read by its index in the batch ("\x1f<index>" suffix); the
+    // reference prints the read's name (src/mod.c:843,1174)
+    auto die_read = [&](mmc_ctx *c, const BatchMeta &meta) {
+        std::string msg = mmc_strerror(c);
+        const size_t sep = msg.find('\x1f');
+        if (sep != std::string::npos) {
+            const unsigned long idx = strtoul(msg.c_str() + sep + 1, nullptr, 10);
+            msg.resize(sep);
+            const size_t colon = msg.find(": ");
+            if (colon != std::string::npos && idx < meta.qname_off.size()) {
+                std::string text = msg.substr(colon + 2);
+                const std::string hc = "Hard clipping found and";
+                if (text.compare(0, hc.size(), hc) == 0) text = std::string("Hard clipping found in ") + meta.qname((uint32_t)idx) + " and" + text.substr(hc.size());
+                else text = std::string("read_id:") + meta.qname((uint32_t)idx) + " " + text;
+                msg = text;
+            }
+        }
+        ERROR("%s", msg.c_str());
         exit(EXIT_FAILURE);
     };
     int more = 1;
     while (more) {
-        const int si = counter % n_slots;
-        if (ring[si]) {                                   // recycle the oldest slot (joins the "previous processor")
-            if (mmc_batch_release(ctx, ring[si]) != MMC_OK) die_read(ring[si], metas[si]);
-            ring[si] = nullptr;
+        int d = 0;
+        if (ndev > 1) {                                   // the device that owns the next record
+            d = loader.next_owner(&err);
+            if (d == -2) { ERROR("%s", err.c_str()); exit(EXIT_FAILURE); }
+            if (d < 0) d = 0;
+        }
+        mmc_ctx *c = ctxs[d];
+        Ring &rg = rings[d];
+        const int si = rg.next; rg.next = (rg.next + 1) % n_slots;
+        if (rg.b[si]) {                                   // recycle the oldest slot (joins the "previous processor")
+            if (mmc_batch_release(c, rg.b[si]) != MMC_OK) die_read(c, rg.meta[si]);
+            rg.b[si] = nullptr;
         }
         mmc_batch_t *b = nullptr;
-        if (mmc_batch_acquire(ctx, &b) != MMC_OK) { ERROR("%s", mmc_strerror(ctx)); exit(EXIT_FAILURE); }
+        if (mmc_batch_acquire(c, &b) != MMC_OK) { ERROR("%s", mmc_strerror(c)); exit(EXIT_FAILURE); }
         double t0 = realtime();
-        more = loader.fill(b, &metas[si], &err);
+        more = loader.fill(b, &rg.meta[si], &err);
         load_time += realtime() - t0;
         if (more < 0) { ERROR("%s", err.c_str()); exit(EXIT_FAILURE); }
-        const BatchStats &st = metas[si].stats;
+        const BatchStats &st = rg.meta[si].stats;
         fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bases) loaded\n", func, realtime() - realtime0,
                 cputime() / (realtime() - realtime0), st.n_recs, st.processed_bytes / (1000.0 * 1000.0));
-        if (mmc_batch_submit(ctx, b) != MMC_OK) { ERROR("%s", mmc_strerror(ctx)); exit(EXIT_FAILURE); }
-        ring[si] = b;
+        if (mmc_batch_submit(c, b) != MMC_OK) { ERROR("%s", mmc_strerror(c)); exit(EXIT_FAILURE); }
+        rg.b[si] = b;
         if (subtool == MMC_VIEW) {
             const mmc_view_rec_t *recs = nullptr; uint64_t n = 0;
-            if (mmc_view_fetch(ctx, b, &recs, &n) != MMC_OK) die_read(b, metas[si]);
+            if (mmc_view_fetch(c, b, &recs, &n) != MMC_OK) die_read(c, rg.meta[si]);
             double o0 = realtime();
-            print_view_records(opt.out, oo, bam.names, b, metas[si], recs, n, code_names());
+            print_view_records(opt.out, oo, bam.names, b, rg.meta[si], recs, n, code_names_of(c));
             output_time += realtime() - o0;
         }
         fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bytes) processed\t%d Entries (%.1fM bytes) skipped\n", func,
@@ -285,23 +361,78 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         if (opt.debug_break == counter) break;
         counter++;
     }
-    for (int i = 0; i < n_slots; ++i)
-        if (ring[i] && mmc_batch_release(ctx, ring[i]) != MMC_OK) die_read(ring[i], metas[i]);
+    for (int d = 0; d < ndev; ++d)
+        for (int i = 0; i < n_slots; ++i)
+            if (rings[d].b[i] && mmc_batch_release(ctxs[d], rings[d].b[i]) != MMC_OK) die_read(ctxs[d], rings[d].meta[i]);
 
-    double sort_time = 0;
+    double sort_time = 0, halo_ms = 0;
+    uint64_t halo_bytes = 0;
     if (subtool == MMC_FREQ) {
-        const mmc_freq_rec_t *recs = nullptr; uint64_t n = 0;
         double s0 = realtime();
-        if (mmc_freq_finalize(ctx, &recs, &n) != MMC_OK) { ERROR("%s", mmc_strerror(ctx)); exit(EXIT_FAILURE); }
+        if (big_tid >= 0 && mmc_region_reduce(ctxs.data(), ndev, big_tid, &halo_ms, &halo_bytes) != MMC_OK) {
+            ERROR("%s", mmc_strerror(ctxs[0])); exit(EXIT_FAILURE);
+        }
+        // every device's table; code ids (dictionary order with a '*' code) are translated to one list
+        std::vector<mmc_freq_rec_t> all;
+        std::vector<std::string> codes;
+        const mmc_freq_rec_t *recs = nullptr; uint64_t n = 0;
+        for (int d = 0; d < ndev; ++d) {
+            if (mmc_freq_finalize(ctxs[d], &recs, &n) != MMC_OK) { ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE); }
+            if (ndev == 1) break;
+            const std::vector<std::string> cn = code_names_of(ctxs[d]);
+            std::vector<int> remap(256, -1);
+            const size_t at = all.size();
+            all.insert(all.end(), recs, recs + n);
+            for (size_t i = at; i < all.size(); ++i) {
+                int &m = remap[all[i].code];
+                if (m < 0) {
+                    size_t k = 0;
+                    while (k < codes.size() && codes[k] != cn[all[i].code]) ++k;
+                    if (k == codes.size()) codes.push_back(cn[all[i].code]);
+                    if (k > 255) { ERROR("%s", "more than 256 distinct modification codes across devices"); exit(EXIT_FAILURE); }
+                    m = (int)k;
+                }
+                all[i].code = (uint8_t)m;
+            }
+        }
+        if (ndev > 1) {
+            auto key_less = [](const mmc_freq_rec_t &x, const mmc_freq_rec_t &y) {
+                if (x.tid != y.tid) return x.tid < y.tid;
+                if (x.pos != y.pos) return x.pos < y.pos;
+                if (x.strand != y.strand) return x.strand < y.strand;
+                if (x.code != y.code) return x.code < y.code;
+                if (x.ins_offset != y.ins_offset) return x.ins_offset < y.ins_offset;
+                return x.hap < y.hap;
+            };
+            if (big_tid >= 0) {
+                // region sharding: rows of the cut contig come from several devices and sparse rows (insertions, exotic
+                // haplotypes) of a boundary may exist on both sides: order everything and add rows with equal keys
+                std::stable_sort(all.begin(), all.end(), key_less);
+                size_t w = 0;
+                for (size_t i = 0; i < all.size(); ++i) {
+                    if (w && !key_less(all[w - 1], all[i]) && !key_less(all[i], all[w - 1])) { all[w - 1].n_called += all[i].n_called; all[w - 1].n_mod += all[i].n_mod; }
+                    else all[w++] = all[i];
+                }
+                all.resize(w);
+            }
+            codes.resize(256);
+            recs = all.data(); n = all.size();
+        }
         sort_time = realtime() - s0;
         double o0 = realtime();
-        print_freq_records(opt.out, oo, bam.names, recs, n, code_names());
+        print_freq_records(opt.out, oo, bam.names, recs, n, ndev > 1 ? codes : code_names_of(ctx));
         output_time += realtime() - o0;
     }
     if (opt.out != stdout) fclose(opt.out); else fflush(stdout);
 
     mmc_timers_t tm;
-    mmc_get_timers(ctx, &tm);
+    memset(&tm, 0, sizeof(tm));
+    for (int d = 0; d < ndev; ++d) {
+        mmc_timers_t t1;
+        mmc_get_timers(ctxs[d], &t1);
+        tm.decode_ms = std::max(tm.decode_ms, t1.decode_ms); tm.finalize_ms = std::max(tm.finalize_ms, t1.finalize_ms);
+        tm.h2d_ms = std::max(tm.h2d_ms, t1.h2d_ms); tm.h2d_bytes += t1.h2d_bytes; tm.kernel_launches += t1.kernel_launches;
+    }
     fprintf(stderr, "[%s] total entries: %ld", func, (long)total_reads);
     fprintf(stderr, "\n[%s] total bytes: %.1f M", func, total_bytes / (float)(1000 * 1000));
     fprintf(stderr, "\n[%s] total skipped entries: %ld", func, (long)(total_reads - processed_reads));
@@ -317,8 +448,10 @@ static int run_tool(int subtool, int argc, char *argv[]) {
     fprintf(stderr, "\n[%s] Data output time: %.3f sec", func, output_time);
     fprintf(stderr, "\n[%s] Device: H2D %.3f sec (%.1f MB), %lu kernel launches", func, tm.h2d_ms / 1e3, tm.h2d_bytes / 1e6,
             (unsigned long)tm.kernel_launches);
+    if (ndev > 1) fprintf(stderr, "\n[%s] Devices: %d (%s); boundary reduce %.3f ms, %.1f MB", func, ndev,
+                          big_tid >= 0 ? "longest contig cut by read start, the others dealt by length" : "contigs dealt by length", halo_ms, halo_bytes / 1e6);
     fprintf(stderr, "\n");
-    mmc_destroy(ctx);
+    for (mmc_ctx *c : ctxs) mmc_destroy(c);
     return 0;
 }
 

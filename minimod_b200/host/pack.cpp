@@ -128,10 +128,26 @@ PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt
     return kPacked;
 }
 
+int BatchLoader::next_owner(std::string *err) {
+    for (;;) {
+        if (!has_pending_) {
+            if (eof_) return -1;
+            int rc = bam_->next(&pending_);
+            if (rc == 0) { eof_ = true; return -1; }
+            if (rc < 0) { if (err) *err = "truncated or corrupt BAM record"; return -2; }
+            has_pending_ = true;
+        }
+        const int o = owner_ ? owner_(pending_) : 0;
+        if (o >= 0 || !owner_) return o;
+        return -1;                                      // a record nobody owns (unmapped): it rides along with whatever batch comes next
+    }
+}
+
 int BatchLoader::fill(mmc_batch_t *b, BatchMeta *meta, std::string *err) {
     b->n_reads = 0; b->cigar_used = b->seq_used = b->mm_used = b->ml_used = 0; b->seq_exc_used = 0;
     meta->stats = BatchStats(); meta->qname_off.clear(); meta->qnames.clear();
     BatchStats &st = meta->stats;
+    int batch_owner = -1;
     // while (n_bam_recs < cap && processed_bytes < batch_size_bases), src/minimod.c:249
     while (st.n_recs < opt_.batch_size && st.processed_bytes < opt_.batch_size_bases) {
         if (!has_pending_) {
@@ -140,6 +156,13 @@ int BatchLoader::fill(mmc_batch_t *b, BatchMeta *meta, std::string *err) {
             if (rc == 0) { eof_ = true; return 0; }
             if (rc < 0) { if (err) *err = "truncated or corrupt BAM record"; return -1; }
             has_pending_ = true;
+        }
+        if (owner_) {                                   // the batch ends where the owning device changes
+            const int o = owner_(pending_);
+            if (o >= 0) {
+                if (batch_owner < 0) batch_owner = o;
+                else if (o != batch_owner) return 1;
+            }
         }
         PackResult pr = pack_record(pending_, b, opt_, meta);
         if (pr == kNoSpace) {

@@ -3,6 +3,7 @@
 #ifndef MMH_PACK_H
 #define MMH_PACK_H
 #include <stdint.h>
+#include <functional>
 #include <string>
 #include <vector>
 #include "bam.h"
@@ -44,7 +45,13 @@ public:
     BatchLoader(BamFile *bam, const LoadOpts &opt) : bam_(bam), opt_(opt) {}
     // Fill `b` (reset first).  Returns 1 if more records may follow, 0 at end of file, <0 on error.
     int fill(mmc_batch_t *b, BatchMeta *meta, std::string *err);
+    // Multi-device runs: owner(record) names the device context a record belongs to (< 0: any).  A batch then ends where the
+    // owner changes (a coordinate-sorted BAM changes owner a few hundred times at most), and next_owner() tells the caller
+    // which context to acquire the next batch from (-1: none known yet / end of file).
+    void set_owner(std::function<int(const BamRecord &)> fn) { owner_ = std::move(fn); }
+    int next_owner(std::string *err);
 private:
+    std::function<int(const BamRecord &)> owner_;
     BamFile *bam_;
     LoadOpts opt_;
     BamRecord pending_;

@@ -51,6 +51,7 @@ static SynthConfig config_of(int id) {
     case 4: return {4, 2, 50000, 0, 50000, 50000, 13000, 27000, 10000, 50000, 2, 30.0};
     case 5: return {5, 1, 12000, 15000, 200, 300000, 13000, 27000, 10000, 50000, 0, 30.0};
     case 6: return {6, 1, 8000, 10000, 200, 200000, 13000, 27000, 10000, 50000, 3, 30.0};   // C3 variant with '.' status (Q9)
+    case 7: return {7, 2, 1300000, 0, 1300000, 1300000, 13000, 27000, 10000, 50000, 0, 30.0};   // ultra-long ONT: > 65535 CIGAR ops (CG:B,I tag)
     default: return {id, 0, 15000, 2000, 5000, 25000, 500, 900, 1000, 0, 0, 30.0};
     }
 }
@@ -394,6 +395,22 @@ int mmh_synth_write_bam(void *h, const char *path, uint64_t first, uint64_t coun
             th.emplace_back([&, t]() { for (uint64_t i = (uint64_t)t; i < n; i += (uint64_t)n_threads) s->make_read(first + done + i, &recs[i]); });
         for (auto &x : th) x.join();
         for (uint64_t i = 0; i < n; ++i) {
+            if (recs[i].n_cigar > 65535u) {                                    // SAM spec 4.2.2: placeholder CIGAR + CG:B,I tag
+                BamRecord &w = recs[i];
+                uint32_t ref_len = 0;
+                for (uint32_t k = 0; k < w.n_cigar; ++k) { uint32_t c; memcpy(&c, w.cigar() + 4 * k, 4); uint32_t op = c & 15u; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += c >> 4; }
+                std::vector<uint8_t> d(w.data.begin(), w.data.begin() + w.l_qname);
+                const uint32_t fake[2] = {((uint32_t)w.l_qseq << 4) | 4u, (ref_len << 4) | 3u};
+                d.insert(d.end(), (const uint8_t *)fake, (const uint8_t *)fake + 8);
+                d.insert(d.end(), w.seq(), w.end());
+                const uint8_t hdr[4] = {'C', 'G', 'B', 'I'};
+                d.insert(d.end(), hdr, hdr + 4);
+                const uint32_t n = w.n_cigar;
+                d.insert(d.end(), (const uint8_t *)&n, (const uint8_t *)&n + 4);
+                d.insert(d.end(), w.cigar(), w.cigar() + 4 * (size_t)n);
+                w.l_data = (int32_t)d.size(); d.resize(d.size() + 8, 0);
+                w.data.swap(d); w.n_cigar = 2;
+            }
             const BamRecord &r = recs[i];
             uint8_t fx[36];
             uint32_t block = 32 + (uint32_t)r.l_data;

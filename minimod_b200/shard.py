@@ -60,33 +60,64 @@ def dense_tensor(lib, ctx, tid, start, end, cuda):
     return torch.from_numpy(arr)
 
 
-def exchange_halos(lib, ctx, tid, bounds, rank, dist, cuda):
-    """After all batches: sum every boundary's halo cells across ranks so that the slice owner holds the
-    complete counts.  Returns the halo width used (positions)."""
+def slice_bounds(contig_len, n_ranks):
+    """[start, end) of the positions rank k owns under the rule owner(p) = p * n_ranks // contig_len (the rule
+    mmc_region_reduce() and `minimod --shard-regions` use)."""
+    starts = [(k * contig_len + n_ranks - 1) // n_ranks for k in range(n_ranks)] + [contig_len]
+    return [(starts[k], starts[k + 1]) for k in range(n_ranks)]
+
+
+def exchange_halos(lib, ctx, tid, bounds, rank, dist, cuda, stats=None):
+    """After all batches: move every boundary's counts to the rank that owns the positions.  Rank k holds the reads that
+    start in bounds[k]; a read may run past its slice (even across a whole slice), so for every owner j the cells of
+    [start_j, min(end_j, reach_j)) -- reach_j = how far the reads of ranks < j ran -- are summed over all ranks (one
+    all-reduce per boundary: NCCL on GPUs, gloo in the CPU tests), kept by rank j and zeroed everywhere else.  The regions
+    of different owners are disjoint, so no cell is ever summed twice.  Sparse rows (insertions, exotic haplotypes) of a
+    halo stay on the rank that counted them: merge_rows() adds rows with equal keys when the tables are put together.
+    Returns the widest halo (positions)."""
     import torch
-    world = len(bounds)
+    world = dist.get_world_size()
     lo, hi = C.c_uint32(), C.c_uint32()
     if lib.mmc_touched_range(ctx, tid, C.byref(lo), C.byref(hi)) != 0:
         raise RuntimeError(lib.mmc_strerror(ctx).decode())
-    over = max(0, int(hi.value) - bounds[rank][1])
-    t = torch.tensor([over], dtype=torch.int64, device="cuda" if cuda else "cpu")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    halo = int(t.item())
-    if halo == 0:
-        return 0
-    contig_len = bounds[-1][1]
-    for k in range(world - 1):                       # boundary between rank k and k+1
-        s = bounds[k][1]
-        e = min(contig_len, s + halo)
+    mine = torch.tensor([int(lo.value), int(hi.value)], dtype=torch.int64, device="cuda" if cuda else "cpu")
+    spans = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(spans, mine)
+    spans = [(int(t[0]), int(t[1])) for t in spans]
+    if bounds is None:                                   # reads were dealt by index, not by position: rank j owns from its first read on
+        starts = [0] + [spans[j][0] if spans[j][1] > spans[j][0] else None for j in range(1, world)]
+        for j in range(world - 1, 0, -1):                # a rank without reads owns nothing: its slice collapses onto the next start
+            if starts[j] is None:
+                starts[j] = starts[j + 1] if j + 1 < world else max(sp[1] for sp in spans)
+        bounds = [(starts[j], starts[j + 1] if j + 1 < world else 1 << 62) for j in range(world)]
+    widest, reach = 0, 0
+    for j in range(1, world):
+        if spans[j - 1][1] > spans[j - 1][0]:
+            reach = max(reach, spans[j - 1][1])
+        s, e = bounds[j][0], min(bounds[j][1], reach)
+        if e <= s:
+            continue
         cells = dense_tensor(lib, ctx, tid, s, e, cuda)
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-        if rank != k and e > s:                      # everyone but the left neighbour now holds the full halo;
-            lib.mmc_dense_touch(ctx, tid, s, e)      # the owner (k+1, or further right for very long reads) emits it
-    return halo
+        if rank == j:
+            lib.mmc_dense_touch(ctx, tid, s, e)
+        else:
+            cells.zero_()
+        widest = max(widest, e - s)
+        if stats is not None:
+            stats["bytes"] = stats.get("bytes", 0) + cells.numel() * 8
+    return widest
 
 
-def owned_rows(rows, tid, bounds, rank):
-    """Rows of the final table this rank is responsible for printing."""
-    s, e = bounds[rank]
-    keep = (rows["tid"] != tid) | ((rows["pos"] >= s) & (rows["pos"] < e))
-    return rows[keep]
+def merge_rows(parts):
+    """Union of the ranks' freq tables (lists of canonical row tuples (tid, pos, strand, code, ins, hap, n_called, n_mod)):
+    rows with equal keys -- sparse rows counted on both sides of a boundary -- are added."""
+    acc = {}
+    for part in parts:
+        for r in part:
+            k = tuple(r[:6])
+            if k in acc:
+                acc[k] = (acc[k][0] + r[6], acc[k][1] + r[7])
+            else:
+                acc[k] = (r[6], r[7])
+    return sorted(k + v for k, v in acc.items())

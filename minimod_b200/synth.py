@@ -12,6 +12,7 @@ CONFIG_ARGS = {           # the reference command line each synthetic config is 
     4: dict(mod_codes="m[*],a[A]", haplotypes=True),
     5: dict(mod_codes="m[CG]", mod_thresh="0.8"),
     6: dict(mod_codes="m[CG],h[CG]", mod_thresh="0.8,0.7", insertions=True),
+    7: dict(mod_codes="m[CG]", mod_thresh="0.8"),       # ultra-long ONT reads: > 65535 CIGAR ops travel in a CG:B,I tag
 }
 
 

@@ -97,6 +97,34 @@ void bam_destroy1(bam1_t *b) {
     free(b);
 }
 
+/* htslib >= 1.7 (bam_tag2cigar, called by bam_read1): a CIGAR of more than 65535 ops travels as <l_seq>S<ref_len>N plus a
+ * CG:B,I tag; the real ops are put back and the tag is removed. */
+static void shim_tag2cigar(bam1_t *b) {
+    bam1_core_t *c = &b->core;
+    if (c->n_cigar == 0 || c->tid < 0 || c->pos < 0) return;
+    uint32_t *cigar0 = bam_get_cigar(b);
+    if (bam_cigar_op(cigar0[0]) != BAM_CSOFT_CLIP || (int32_t)bam_cigar_oplen(cigar0[0]) != c->l_qseq) return;
+    uint8_t *CG = bam_aux_get(b, "CG");
+    if (!CG || CG[0] != 'B' || CG[1] != 'I') return;
+    uint32_t n = le32(CG + 2);
+    if (n < c->n_cigar || n >= (1u << 29)) return;
+    size_t fake = 4 * (size_t)c->n_cigar, real = 4 * (size_t)n;
+    uint8_t *tag0 = CG - 2, *tag1 = CG + 6 + real, *end = b->data + b->l_data;
+    if (tag1 > end) return;
+    size_t new_len = (size_t)b->l_data - fake + real - (size_t)(tag1 - tag0) + real * 0;
+    uint8_t *d = (uint8_t *)malloc(new_len + real + 16), *p = d;
+    size_t qn = (size_t)c->l_qname;
+    memcpy(p, b->data, qn); p += qn;
+    memcpy(p, CG + 6, real); p += real;
+    size_t mid = (size_t)(tag0 - (b->data + qn + fake));
+    memcpy(p, b->data + qn + fake, mid); p += mid;
+    memcpy(p, tag1, (size_t)(end - tag1)); p += end - tag1;
+    memset(p, 0, 8);
+    free(b->data);
+    b->data = d; b->l_data = (int)(p - d); b->m_data = (uint32_t)(new_len + real + 16);
+    c->n_cigar = n;
+}
+
 int sam_read1(htsFile *fp, bam_hdr_t *h, bam1_t *b) {
     (void)h;
     uint8_t b4[4], fixed[32];
@@ -125,6 +153,7 @@ int sam_read1(htsFile *fp, bam_hdr_t *h, bam1_t *b) {
     }
     if (b->l_data && read_exact(fp->gz, b->data, (size_t)b->l_data)) return -5;
     memset(b->data + b->l_data, 0, 8);
+    shim_tag2cigar(b);
     return (int)block_size;
 }
 

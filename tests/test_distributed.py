@@ -38,48 +38,63 @@ from parity import Pair
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 lib = N.load_cuda(os.path.join({root!r}, "tests/kernel_emul/_build/libminimod_emul.so"))
-clen = 150000
-s = Synth(3, contigs=(("chrS", clen),), coverage=3.0)
-ca = CONFIG_ARGS[3]
+config, clen, insertions = {config!r}, {clen!r}, {insertions!r}
+s = Synth(config, contigs=(("chrS", clen),), coverage=3.0)
+ca = CONFIG_ARGS[config]
 p, n = s.ref(0)
 ref = C.string_at(p, n)
-cut = clen * 2 // 5                  # not the middle: the synthetic contig has an N run there that no read crosses
-bounds = [(0, cut), (cut, clen)]
-pair = Pair(lib, "freq", [("chrS", ref)], "m[CG],h[CG]", "0.8,0.7", max_reads=s.n_reads + 8, max_bytes=32 << 20)
+bounds = shard.slice_bounds(clen, world)
+kw = dict(insertions=insertions, haplotypes=bool(ca.get("haplotypes")), max_reads=s.n_reads + 8, max_bytes=64 << 20)
+pair = Pair(lib, "freq", [("chrS", ref)], ca["mod_codes"], ca.get("mod_thresh"), **kw)
 # pack everything, then keep only the reads whose start this rank owns (reads are coordinate sorted)
-full = Pair(lib, "freq", [("chrS", ref)], "m[CG],h[CG]", "0.8,0.7", max_reads=s.n_reads + 8, max_bytes=32 << 20)
+full = Pair(lib, "freq", [("chrS", ref)], ca["mod_codes"], ca.get("mod_thresh"), **kw)
 s.fill(full.batch, 0, s.n_reads, 2)
 starts = [full.batch.contents.pos[i] for i in range(full.batch.contents.n_reads)]
-mine = [i for i, st in enumerate(starts) if shard.owner_of(st, bounds) == rank]
-assert mine and mine == list(range(mine[0], mine[-1] + 1))
-s.fill(pair.batch, mine[0], len(mine), 2)
-rc, msg = pair.run_device(); assert rc == 0, msg
+mine = [i for i, st in enumerate(starts) if min(world - 1, st * world // clen) == rank]
+if mine:
+    assert mine == list(range(mine[0], mine[-1] + 1))
+    s.fill(pair.batch, mine[0], len(mine), 2)
+    rc, msg = pair.run_device(); assert rc == 0, msg
 halo = shard.exchange_halos(lib, pair.ctx, 0, bounds, rank, dist, cuda=False)
-rows = pair.device_freq()
-own = [r for r in rows if bounds[rank][0] <= r[1] < bounds[rank][1]]
+rows = pair.device_freq() if mine else []
 gathered = [None] * world
-dist.all_gather_object(gathered, own)
+dist.all_gather_object(gathered, (rows, halo))
 if rank == 0:
     rc, msg = full.run_device(); assert rc == 0, msg
     single = full.device_freq()
-    merged = sorted(r for part in gathered for r in part)
-    assert halo > 1000, halo          # reads do run across the boundary
-    assert merged == single, (len(merged), len(single))
-    print("OK", len(single), "rows; halo", halo)
+    merged = shard.merge_rows([part for part, _ in gathered])
+    assert max(h for _, h in gathered) > {min_halo!r}, gathered[0][1]     # reads do run across the boundaries
+    assert merged == single and len(single) > 1000, (len(merged), len(single))
+    print("OK", len(single), "rows; halo", max(h for _, h in gathered))
 dist.destroy_process_group()
 '''
 
 
-def test_region_sharding_two_ranks_gloo(emul_lib, tmp_path):
+def _run_region(tmp_path, world, port, **fmt):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", WORLD_SIZE="2")
+    script.write_text(WORKER.format(root=ROOT, **fmt))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world))
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-             for r in range(2)]
-    outs = [p.communicate(timeout=600) for p in procs]
+             for r in range(world)]
+    outs = [p.communicate(timeout=900) for p in procs]
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e.decode()[-3000:]
     assert b"OK" in outs[0][0]
+
+
+def test_region_sharding_three_ranks_gloo(emul_lib, tmp_path):
+    # (three slices: the synthetic contig has an N run in its middle that no read crosses)
+    _run_region(tmp_path, 3, 29617, config=3, clen=150000, insertions=False, min_halo=1000)
+
+
+def test_region_sharding_insertions_three_ranks_gloo(emul_lib, tmp_path):
+    """--insertions: sparse rows sit on both sides of a boundary and must be added, not dropped."""
+    _run_region(tmp_path, 3, 29637, config=3, clen=150000, insertions=True, min_halo=1000)
+
+
+def test_region_sharding_halo_wider_than_slice_gloo(emul_lib, tmp_path):
+    """50 kb reads over 30 kb slices: a read's counts cross two boundaries; every cell must be summed exactly once."""
+    _run_region(tmp_path, 4, 29647, config=4, clen=120000, insertions=False, min_halo=20000)
 
 
 # ---- contig sharding (BASELINE config 5 shape): GRCh38-like contig table scaled down, contigs dealt to ranks by LPT,
