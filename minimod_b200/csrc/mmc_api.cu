@@ -61,11 +61,11 @@ struct Slot {
     WRead *d_reads = nullptr;                  // flat path: per-read state
     uint32_t *d_pool = nullptr; size_t pool_words = 0;      // flat path: scratch pool
     unsigned long long *h_state = nullptr;     // pinned mirror
-    ViewDev *d_view = nullptr;
+    ViewDev *d_view = nullptr; uint64_t view_cap = 0;    // VIEW: rows of one batch; regrown (and the batch re-run) when it overflows
     uint32_t *d_scratch = nullptr;
     size_t scratch_words = 0;
     std::vector<mmc_view_rec_t> view_out;
-    bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false;
+    bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false, view_regrown = false;
     uint32_t n_reads_submitted = 0;
     uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
     bool use_stream = false;                   // this batch goes through k_decode_stream (long CIGARs / long reads) instead of k_decode_warp<PRE>
@@ -238,7 +238,7 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cudaMalloc((void **)&s.d_defer_flat, sizeof(uint32_t) * std::max<size_t>(1, R)));
     if (ctx->split_path || ctx->stream_path) CU(ctx, cudaMalloc((void **)&s.d_reads, sizeof(WRead) * std::max<size_t>(1, R)));
     CU(ctx, cudaMalloc((void **)&s.d_defer, sizeof(uint32_t) * std::max<size_t>(1, R)));
-    if (o.subtool == MMC_VIEW) CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev)));
+    if (o.subtool == MMC_VIEW) { CU(ctx, cudaMalloc((void **)&s.d_view, ctx->view_cap * sizeof(ViewDev))); s.view_cap = ctx->view_cap; }
     mmc_batch_t &b = s.pub;
     memset(&b, 0, sizeof(b));
     b.max_reads = (uint32_t)R;
@@ -445,7 +445,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     P.n_code_slots = ctx->n_code_slots; P.n_hap_slots = ctx->n_hap_slots;
     P.touch_lo = ctx->d_touch; P.touch_hi = ctx->d_touch + ctx->contigs.size();
     P.sparse = ctx->d_sparse; P.sparse_cap = ctx->sparse_cap; P.sparse_n = ctx->d_sparse_n;
-    P.view = s.d_view; P.view_cap = ctx->view_cap; P.view_n = s.d_state + 1;
+    P.view = s.d_view; P.view_cap = s.view_cap; P.view_n = s.d_state + 1;
     P.err = s.d_state;
     P.scratch = per_cta ? s.d_scratch : nullptr;
     P.scratch_words_per_cta = per_cta; P.scratch_cig_words = cig_words;
@@ -566,9 +566,24 @@ int wait_slot(mmc_ctx *ctx, Slot &s) {
         ctx->err += "\x1f" + std::to_string(read);           // machine-readable suffix: \x1f<read index>
         return MMC_EREAD;
     }
-    if (ctx->opts.subtool == MMC_VIEW && s.h_state[1] > ctx->view_cap)
-        return fail(ctx, MMC_ENOMEM, "view record buffer overflow (%llu > %llu); raise view_capacity",
-                    (unsigned long long)s.h_state[1], (unsigned long long)ctx->view_cap);
+    if (ctx->opts.subtool == MMC_VIEW && s.n_reads_submitted && s.h_state[1] > s.view_cap) {
+        // more rows than the slot's buffer holds ('.' blocks with a `*` context can emit a row per base): view rows have no
+        // side effect outside the slot, so grow the buffer to the count the kernels reported and run the batch again
+        const uint64_t want = s.h_state[1] + s.h_state[1] / 16 + 1024;
+        if (s.view_regrown) return fail(ctx, MMC_ENOMEM, "view record buffer overflow (%llu rows > %llu) after regrowing it",
+                                        (unsigned long long)s.h_state[1], (unsigned long long)s.view_cap);
+        if (s.d_view) CU(ctx, cudaFree(s.d_view));
+        s.d_view = nullptr; s.view_cap = 0;
+        if (cudaMalloc((void **)&s.d_view, want * sizeof(ViewDev)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, MMC_ENOMEM, "cannot grow the view record buffer to %llu rows", (unsigned long long)want);
+        }
+        s.view_cap = want; s.view_regrown = true;
+        int rc = launch_decode(ctx, s);
+        if (rc == MMC_OK) rc = wait_slot(ctx, s);
+        s.view_regrown = false;
+        return rc;
+    }
     return MMC_OK;
 }
 
@@ -1462,6 +1477,7 @@ int mmc_region_reduce(mmc_ctx *const *ctxs, int32_t n_ctx, int32_t tid, double *
     init_all_t p_init = nullptr; allreduce_t p_ar = nullptr; void_t p_gs = nullptr, p_ge = nullptr; destroy_t p_destroy = nullptr; errstr_t p_err = nullptr;
     std::vector<comm_t> comms(n_ctx, nullptr);
     if (!same_device) {
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);         // stdout is the tool's data channel: NCCL's version / debug lines go to stderr
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!h) return fail(c0, MMC_ECUDA, "mmc_region_reduce: contexts on several devices need NCCL, but libnccl.so.2 cannot be loaded (%s)", dlerror());
         p_init = (init_all_t)dlsym(h, "ncclCommInitAll"); p_ar = (allreduce_t)dlsym(h, "ncclAllReduce");

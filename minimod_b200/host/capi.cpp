@@ -87,7 +87,7 @@ const char *mmh_loader_qname(void *h, uint32_t i) {
 void *mmh_fasta_load(const char *path, char *err, int errlen) {
     Fasta *f = new Fasta();
     std::string e;
-    if (!read_fasta(path, &f->recs, &e)) { set_err(err, errlen, e); delete f; return nullptr; }
+    if (!read_fasta(path, &f->recs, &e, 8)) { set_err(err, errlen, e); delete f; return nullptr; }
     return f;
 }
 void mmh_fasta_free(void *h) { delete (Fasta *)h; }

@@ -7,6 +7,7 @@
 #include <vector>
 namespace mmh {
 struct FastaRecord { std::string name, seq; };
-bool read_fasta(const std::string &path, std::vector<FastaRecord> *out, std::string *err);
+// threads > 1: plain FASTA files are mapped and parsed record-parallel; gzip / FASTQ input falls back to the serial reader
+bool read_fasta(const std::string &path, std::vector<FastaRecord> *out, std::string *err, int threads = 1);
 }
 #endif

@@ -24,3 +24,23 @@ def test_edge_cases_emulated_two_bit_seq(emul_lib, monkeypatch):
         run_case(emul_lib, case)
     for case in FATAL:
         run_fatal(emul_lib, case)
+
+
+def test_view_buffer_regrows(emul_lib):
+    """A view batch with more rows than the slot's record buffer: the buffer is regrown and the batch re-run
+    (it used to fail with 'raise view_capacity', an option the CLI does not have)."""
+    import ctypes as C
+    from minimod_b200.synth import Synth
+    from parity import Pair
+    s = Synth(6, contigs=(("chrS", 60000),), coverage=1.0)
+    p, n = s.ref(0)
+    pair = Pair(emul_lib, "view", [("chrS", C.string_at(p, n))], "m[*],h[*]", None, max_reads=s.n_reads + 8, max_bytes=8 << 20, view_capacity=7)
+    try:
+        got, _ = s.fill(pair.batch, 0, s.n_reads, 2)
+        assert got == s.n_reads
+        rc, msg = pair.run_device(); assert rc == 0, msg
+        orc, omsg = pair.run_oracle(); assert orc == 0, omsg
+        d, o = pair.device_view(), pair.oracle_view()
+        assert len(d) > 100 and d == o
+    finally:
+        pair.close(); s.close()

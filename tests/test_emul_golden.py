@@ -39,6 +39,8 @@ PATHS = [("warp", None), ("general", None), ("split", "4608"), ("warp", "4400"),
 @pytest.mark.parametrize("path,arena", PATHS, ids=[f"{p}-{a or 'default'}" for p, a in PATHS])
 @pytest.mark.parametrize("name", ["test7.tsv", "test5a.tsv", "test17a.tsv", "test16.tsv", "test5c.tsv"])
 def test_decode_paths_agree(emul_lib, monkeypatch, path, arena, name):
+    if path != "stream" and name in ("test16.tsv", "test5c.tsv"):
+        pytest.skip("the extra cases are for the streaming kernel; the GPU suite runs every path on every case")
     monkeypatch.setenv("MMC_DECODE_PATH", path)
     if arena:
         monkeypatch.setenv("MMC_WARP_ARENA", arena)

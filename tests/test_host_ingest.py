@@ -58,3 +58,25 @@ def test_corrupt_block_is_an_error_not_a_crash(emul_lib, synth_files, tmp_path):
     open(bad, "wb").write(bytes(blob))
     r = run_cli(cli_args(3) + ["-t", "4"], fa, bad)
     assert r.returncode != 0 and r.returncode > 0                             # exit(EXIT_FAILURE), no signal
+
+
+def test_fasta_mapped_parser_matches_kseq_semantics(host_lib, tmp_path):
+    """Plain FASTA goes through the mapped, record-parallel parser; gzip through the serial one: same records
+    (name up to the first blank, lines joined, CR stripped, a later record of the same name replaces the earlier)."""
+    import ctypes as C
+    import gzip
+    text = (b">ctgA some description\r\nACGTacgt\r\nNNNN\r\n\r\n>ctgB\nTTTT\n>empty\n>ctgA again\nGGGGCCCC\nAAAA" )
+    plain, gz = tmp_path / "x.fa", tmp_path / "x.fa.gz"
+    plain.write_bytes(text)
+    with gzip.open(gz, "wb") as fh:
+        fh.write(text)
+    got = []
+    for path in (plain, gz):
+        err = C.create_string_buffer(256)
+        h = host_lib.mmh_fasta_load(os.fsencode(str(path)), err, 256)
+        assert h, err.value
+        recs = [(host_lib.mmh_fasta_name(h, i), C.string_at(host_lib.mmh_fasta_seq(h, i), host_lib.mmh_fasta_len(h, i)))
+                for i in range(host_lib.mmh_fasta_n(h))]
+        host_lib.mmh_fasta_free(h)
+        got.append(recs)
+    assert got[0] == got[1] == [(b"ctgA", b"GGGGCCCCAAAA"), (b"ctgB", b"TTTT"), (b"empty", b"")]

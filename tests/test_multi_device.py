@@ -18,7 +18,7 @@ CASES = [  # config, contigs, coverage
     (5, (("t2", 300000), ("t10", 200000), ("t1_x", 150000), ("t7", 90000)), 2.0),
     (3, (("big", 400000), ("s1", 100000), ("s2", 60000)), 2.0),          # --insertions: sparse rows on both sides of a boundary
     (6, (("big", 300000), ("s1", 80000)), 1.5),                          # '.' status blocks
-    (4, (("big", 400000), ("s1", 120000)), 1.0),                         # --haplotypes, 50 kb reads: halos wider than a slice
+    (4, (("big", 260000), ("s1", 120000)), 0.7),                         # --haplotypes, 50 kb reads: halos wider than a slice
 ]
 
 
