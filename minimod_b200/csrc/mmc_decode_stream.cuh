@@ -206,7 +206,6 @@ __device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff,
     WTile *T = A.T;
     SRing *G = A.G;
     const uint8_t *seq = R->st.seq;
-    const uint32_t *dirp = R->st.flex + R->st.o_dir;
     SStream Z = *A.Z;
     uint32_t c0 = 0;
     while (c0 < n) {
@@ -252,7 +251,6 @@ __device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff,
         const uint32_t off = wsel + ((rem != 0u || !(f & 0x80u)) ? 1u : 0u);
         uint32_t q = u * 32u + off;
         if (Z.dot) atomicOr(&G->exp[sl], 1u << off);
-        mmc_prefetch_l2(dirp + (q >> 5));                              // the CIGAR directory line phase B will want (stream layout: 32-base buckets)
         if (Z.mode == 1u) {
             const uint32_t o8 = off & 7u, nib = (wv >> (8u * (o8 >> 1) + ((o8 & 1u) ? 0u : 4u))) & 0xfu;
             if (nib != 1u) q |= 0x80000000u;
@@ -328,19 +326,8 @@ __device__ __forceinline__ void s_tail_fast(const DecodeParams &P, WRead *R, WTi
             const uint32_t b = q >> g;
             uint32_t lo = ldg32(dir + b), hi = (((b + 1u) << g) < total_q) ? ldg32(dir + b + 1u) : last_samp;
             const uint32_t qlim = (q + 1u) << 4;
-            // the op of q is one of the few entries from dir[b] on (32-base buckets): four are fetched at once -- two dependent
-            // round trips per call instead of a binary search's chain -- and a longer bucket finishes with the search
-            const uint32_t i1 = lo + 1u < hi ? lo + 1u : hi, i2 = lo + 2u < hi ? lo + 2u : hi, i3 = lo + 3u < hi ? lo + 3u : hi;
-            const uint2 e0 = __ldg(&pr[lo]), e1 = __ldg(&pr[i1]), e2 = __ldg(&pr[i2]), e3 = __ldg(&pr[i3]);
-            uint2 en = e0;                                                              // largest entry with q0 <= q (entries ascend)
-            if (e1.x < qlim) en = e1;
-            if (e2.x < qlim) en = e2;
-            if (e3.x < qlim) en = e3;
-            if (hi > lo + 3u && e3.x < qlim) {
-                lo += 3u;
-                while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (ldg32(&pr[mid].x) < qlim) lo = mid; else hi = mid - 1u; }
-                en = __ldg(&pr[lo]);
-            }
+            while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (ldg32(&pr[mid].x) < qlim) lo = mid; else hi = mid - 1u; }   // 32-base buckets: a step or none
+            const uint2 en = __ldg(&pr[lo]);
             const uint32_t ce = en.x, op = ce & 15u;
             if (op == 0u || op == 7u || op == 8u) ref_pos = (uint32_t)(pos + (int32_t)(en.y + q - (ce >> 4)));
             else if (EX && insertions && op == 1u) {                                    // ins[] / ins_offset (src/mod.c:1122-1127)

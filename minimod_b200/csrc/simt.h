@@ -29,12 +29,10 @@
 // One lane arms the barrier with the byte count and issues the copy; every lane that reads the data waits on the
 // barrier's phase parity.  Under the SIMT emulator the copy is a memcpy and the waits are no-ops.
 #ifdef MMC_EMUL
-static inline void mmc_prefetch_l2(const void *) {}
 static inline void mmc_mbar_init(unsigned long long *bar, uint32_t) { *bar = 0; }
 static inline void mmc_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *) { memcpy(dst, src, bytes); }
 static inline void mmc_mbar_wait(unsigned long long *, uint32_t) {}
 #else
-__device__ __forceinline__ void mmc_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t mmc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mmc_mbar_init(unsigned long long *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mmc_smem_u32(bar)), "r"(count) : "memory");

@@ -21,8 +21,6 @@ CLI = os.path.join(ROOT, "minimod_b200", "bin", "minimod")
 @pytest.mark.parametrize("config,cov", [(2, 4.0), (3, 3.0), (6, 2.0), (4, 1.0), (5, 3.0)])
 @pytest.mark.parametrize("sub", ["freq", "view"])
 def test_synthetic_parity_cuda(cuda_lib, config, cov, sub):
-    if config == 5:
-        pytest.skip("config 5 shares config 2's tag style; covered by test_multi_contig_cli")
     n, st = run_synth(cuda_lib, config, 1500000, cov, sub)
     assert n > 0
 
@@ -140,3 +138,33 @@ def test_multi_contig_cli_vs_reference_binary(tmp_path, config):
         assert sorted_lines(mine.stdout) == sorted_lines(ref.stdout)
     order = [l.split(b"\t")[0] for l in mine.stdout.splitlines() if not l.startswith(b"contig")]
     assert [c for i, c in enumerate(order) if i == 0 or order[i - 1] != c] == [b"t10", b"t1_x", b"t2"]
+
+
+GRCH38_PRIMARY = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422,
+                  135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167,
+                  46709983, 50818468, 156040895, 57227415, 16569]
+
+
+@pytest.mark.skipif(not have_ref_bin(), reason="oracle/_ref/minimod_ref not present")
+@pytest.mark.parametrize("devices", [None, "all"])
+def test_config5_grch38_shaped_vs_reference_binary(tmp_path, devices):
+    """BASELINE config 5 at test size: the 25 primary GRCh38 contigs (lengths / 250) + 6 small ones, ONT 5mC reads at 2x,
+    `freq -c m[CG] -m 0.8` -- the `minimod` binary (one device, and contig-sharded over every device of the box) must be
+    byte-identical to the unmodified reference binary (single-mod context-checked output is tie-free)."""
+    names = ["chr%d" % (i + 1) for i in range(22)] + ["chrX", "chrY", "chrM"] + ["chrUn_%d" % i for i in range(6)]
+    lens = [max(16569, l // 250) for l in GRCH38_PRIMARY] + [40000 + 3000 * i for i in range(6)]
+    s = Synth(5, contigs=tuple(zip(names, lens)), coverage=2.0)
+    assert s.n_reads > 1000
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "reads.bam")
+    s.write_fasta(fa); s.write_bam(bam); s.close()
+    args = cli_args(5)
+    extra = []
+    if devices:
+        import torch
+        n = torch.cuda.device_count()
+        extra = ["--devices", ",".join(str(i) for i in range(n)) if n > 1 else "0,0"]
+    mine = subprocess.run([CLI, "freq"] + args + ["-K", "512"] + extra + [fa, bam], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    ref = subprocess.run([REF_BIN, "freq"] + args + ["-t", "16", "-K", "4092", "-B", "100M", fa, bam], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert mine.returncode == 0, mine.stderr.decode()[-1500:]
+    assert ref.returncode == 0
+    assert mine.stdout == ref.stdout and len(mine.stdout.splitlines()) > 100000
