@@ -34,10 +34,10 @@ def check(binary, name, sub, args, bam, contig, extra=()):
         assert sorted_lines(out) == sorted_lines(gold), name
 
 
-@pytest.mark.skipif(not os.path.exists(EMUL_BIN), reason="oracle/_ref/minimod_ref_emul not built (needs /root/reference)")
 CPU_SUBSET = {"test1.tsv", "test2a.tsv", "test2c.tsv", "test4.bedmethyl", "test5a.tsv", "test5c.tsv", "test7.tsv", "test16.tsv", "test17a.tsv"}
 
 
+@pytest.mark.skipif(not os.path.exists(EMUL_BIN), reason="oracle/_ref/minimod_ref_emul not built (needs /root/reference)")
 @pytest.mark.parametrize("name,sub,args,bam,contig", [c for c in GOLDEN_CASES if c[0] in CPU_SUBSET], ids=[c[0] for c in GOLDEN_CASES if c[0] in CPU_SUBSET])
 def test_reference_with_glue_emulated(emul_lib, name, sub, args, bam, contig):
     """(a representative subset keeps the CPU suite short; the GPU suite runs all 22)"""
