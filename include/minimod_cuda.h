@@ -47,6 +47,7 @@ extern "C" {
 #define MMC_ENOMEM       -3   /* host or device allocation failed / capacity exceeded */
 #define MMC_EREAD        -4   /* a read is malformed in a way the reference treats as fatal */
 #define MMC_ESTATE       -5   /* call sequence error                                  */
+#define MMC_EORDER       -6   /* rows were drained early and a later batch was not in coordinate order */
 
 /* subtool: enum subtool, src/minimod.h:88 */
 #define MMC_VIEW 0
@@ -225,6 +226,24 @@ int  mmc_sync(mmc_ctx *ctx);
 int  mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_recs);
 int  mmc_freq_reset(mmc_ctx *ctx);                            /* zero all counts */
 const char *mmc_code_name(const mmc_ctx *ctx, int32_t code);  /* mod_code string of a row */
+
+/* ---- streaming results for coordinate-sorted input.  The reference prints after the last read
+ *      (output_core, src/minimod.c:388; its BAMs are coordinate-sorted, test/test_ext.sh:63): here the rows of
+ *      finished positions can leave while later batches are still being copied and decoded, so the read-back
+ *      and the text formatting overlap the rest of the job and D2H shares no time with H2D.
+ *      mmc_freq_drain(tid,pos): the caller states that every read it submits FROM NOW ON starts at or after
+ *      (tid,pos) in coordinate order (tid, then pos).  Returns the rows before that watermark that no earlier
+ *      drain returned, in the order mmc_freq_finalize() uses; waits only for the batches that hold a read
+ *      starting before the watermark.  The rows stay valid until the second-next drain/finalize/reset (two
+ *      pinned buffers alternate).  Returns no rows (and moves nothing) while the side buffer holds records
+ *      (--insertions, haplotypes >= dense_haps, code ids >= dense_codes): those runs finalize at the end.
+ *      After drains, mmc_freq_finalize() returns the REMAINING rows: concatenated, the drains and the
+ *      remainder are the single-call table.  Counts are never cleared by a drain, so a broken promise loses
+ *      nothing: the library notices a later batch that starts before the watermark, mmc_freq_finalize() then
+ *      fails with MMC_EORDER, and after mmc_freq_undrain() it returns the complete table (the caller drops the
+ *      rows it drained). ------------------------------------------------------------------ */
+int  mmc_freq_drain(mmc_ctx *ctx, int32_t tid, uint32_t pos, const mmc_freq_rec_t **recs, uint64_t *n_recs);
+int  mmc_freq_undrain(mmc_ctx *ctx);
 
 /* ---- view results: replaces output_db()'s per-read collect (src/mod.c:560-593).  Rows of
  *      the batch, ordered by (read, ref_pos, code, ins_offset) after first-wins

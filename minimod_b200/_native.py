@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(HERE, "lib")
 
 MMC_VIEW, MMC_FREQ = 0, 1
-MMC_OK, MMC_EINVAL, MMC_ECUDA, MMC_ENOMEM, MMC_EREAD, MMC_ESTATE = 0, -1, -2, -3, -4, -5
+MMC_OK, MMC_EINVAL, MMC_ECUDA, MMC_ENOMEM, MMC_EREAD, MMC_ESTATE, MMC_EORDER = 0, -1, -2, -3, -4, -5, -6
 MMC_MAX_CODE_LEN, MMC_MAX_CONTEXT, MMC_MAX_MODS = 8, 32, 64
 
 
@@ -87,6 +87,7 @@ CUDA_SYMBOLS = [
     "mmc_create", "mmc_destroy", "mmc_strerror", "mmc_abi_version", "mmc_ref_add", "mmc_ref_commit",
     "mmc_batch_acquire", "mmc_batch_submit", "mmc_batch_wait", "mmc_batch_release", "mmc_batch_upload",
     "mmc_batch_launch", "mmc_sync", "mmc_freq_finalize", "mmc_freq_reset", "mmc_code_name", "mmc_view_fetch",
+    "mmc_freq_drain", "mmc_freq_undrain",
     "mmc_dense_slice", "mmc_dense_touch", "mmc_touched_range", "mmc_get_timers", "mmc_reset_timers", "mmc_last_decode_ms", "mmc_describe", "mmc_region_reduce",
 ]
 
@@ -110,6 +111,8 @@ def _declare_cuda(lib):
         "mmc_sync": (C.c_int, [vp]),
         "mmc_freq_finalize": (C.c_int, [vp, P(P(MmcFreqRec)), P(u64)]),
         "mmc_freq_reset": (C.c_int, [vp]),
+        "mmc_freq_drain": (C.c_int, [vp, i32, u32, P(P(MmcFreqRec)), P(u64)]),
+        "mmc_freq_undrain": (C.c_int, [vp]),
         "mmc_code_name": (C.c_char_p, [vp, i32]),
         "mmc_view_fetch": (C.c_int, [vp, P(MmcBatch), P(P(MmcViewRec)), P(u64)]),
         "mmc_dense_slice": (C.c_int, [vp, i32, u32, u32, P(vp), P(u64)]),

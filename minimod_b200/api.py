@@ -140,10 +140,39 @@ class Core:
         buf = (N.MmcFreqRec * n.value).from_address(C.addressof(recs.contents))
         return np.frombuffer(buf, dtype=N.FREQ_DTYPE).copy()
 
-    def output_core(self, bedmethyl=False):
+    def drain_records(self, tid, pos):
+        """Rows before the coordinate watermark (tid, pos) that no earlier drain returned (mmc_freq_drain): the caller
+        submits no read starting before it from now on.  Copies them out of the library's alternating buffers."""
+        recs, n = C.POINTER(N.MmcFreqRec)(), C.c_uint64()
+        self._check(self.lib.mmc_freq_drain(self.ctx, int(tid), int(pos), C.byref(recs), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=N.FREQ_DTYPE)
+        buf = (N.MmcFreqRec * n.value).from_address(C.addressof(recs.contents))
+        return np.frombuffer(buf, dtype=N.FREQ_DTYPE).copy()
+
+    def remaining_records(self, drained):
+        """The table after drains: `drained` (list of arrays from drain_records) + what mmc_freq_finalize() still holds.
+        If a batch broke the coordinate order after a drain (MMC_EORDER), the drained rows are dropped and the
+        complete table is read back instead (counts are never cleared by a drain)."""
+        recs, n = C.POINTER(N.MmcFreqRec)(), C.c_uint64()
+        rc = self.lib.mmc_freq_finalize(self.ctx, C.byref(recs), C.byref(n))
+        if rc == N.MMC_EORDER:
+            self._check(self.lib.mmc_freq_undrain(self.ctx))
+            return self.freq_records()
+        self._check(rc)
+        rest = np.zeros(0, dtype=N.FREQ_DTYPE)
+        if n.value:
+            rest = np.frombuffer((N.MmcFreqRec * n.value).from_address(C.addressof(recs.contents)), dtype=N.FREQ_DTYPE).copy()
+        return np.concatenate(list(drained) + [rest]) if drained else rest
+
+    def output_core(self, bedmethyl=False, records=None):
         """freq text exactly as print_freq_header()+print_freq_output() write it."""
         recs, n = C.POINTER(N.MmcFreqRec)(), C.c_uint64()
-        self._check(self.lib.mmc_freq_finalize(self.ctx, C.byref(recs), C.byref(n)))
+        if records is not None:
+            records = np.ascontiguousarray(records)
+            recs, n = C.cast(records.ctypes.data, C.POINTER(N.MmcFreqRec)), C.c_uint64(len(records))
+        else:
+            self._check(self.lib.mmc_freq_finalize(self.ctx, C.byref(recs), C.byref(n)))
         names = (C.c_char_p * max(1, len(self.contig_names)))(*self.contig_names)
         codes = (C.c_char_p * 256)(*self.code_names())
         with tempfile.NamedTemporaryFile(suffix=".tsv", delete=False) as tf:
@@ -180,21 +209,28 @@ class Core:
         return {k: getattr(t, k) for k, _ in N.MmcTimers._fields_}
 
 
-def freq(ref_fa, bam, mod_codes="m", mod_thresh=None, bedmethyl=False, **kw):
-    """`minimod freq` through the C ABI; returns the stdout bytes the reference would print."""
+def freq(ref_fa, bam, mod_codes="m", mod_thresh=None, bedmethyl=False, drain=False, **kw):
+    """`minimod freq` through the C ABI; returns the stdout bytes the reference would print.
+    drain: rows of finished positions leave while later batches are in flight (mmc_freq_drain; coordinate-sorted input,
+    anything else falls back to the single read-back at the end)."""
     with Core("freq", bam, mod_codes, mod_thresh, **kw) as core:
         core.load_ref(ref_fa)
-        held = []
+        held, drained = [], []
         while True:
             b = core.load_db()
             if b is None:
                 break
+            first = (int(b.contents.tid[0]), int(b.contents.pos[0])) if b.contents.n_reads else None
             core.process_db(b)
+            if drain and first is not None and first[0] >= 0:
+                drained.append(core.drain_records(*first))     # every later read starts at or after this batch's first
             held.append(b)
             if len(held) >= 3:
                 core.free_db(held.pop(0))
         for b in held:
             core.free_db(b)
+        if drain:
+            return core.output_core(bedmethyl=bedmethyl, records=core.remaining_records(drained))
         return core.output_core(bedmethyl=bedmethyl)
 
 

@@ -68,6 +68,7 @@ struct Slot {
     bool in_flight = false, uploaded = false, acquired = false, timed = false, h2d_pending = false, view_regrown = false;
     uint32_t n_reads_submitted = 0;
     uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
+    uint32_t min_tid = 0xffffffffu, min_pos = 0;   // first read of the batch in coordinate order (analyse_batch; unmapped sorts last)
     bool use_stream = false;                   // this batch goes through k_decode_stream (long CIGARs / long reads) instead of k_decode_warp<PRE>
     int s_ctas = 8; uint32_t s_arena = 0, s_setup_flex = 4608;   // k_decode_stream: CTAs per SM, arena bytes per warp; k_flat_setup's room for dir | cq | cr
 };
@@ -130,6 +131,11 @@ struct mmc_ctx {
     FreqRecDev *d_merged = nullptr; size_t d_merged_cap = 0;         // dense + sparse rows in output order
     unsigned long long *d_sn_rows = nullptr, *h_sn_rows = nullptr;   // number of reduced sparse rows (device, pinned)
     mmc_freq_rec_t *h_rows = nullptr; size_t h_rows_cap = 0;       // pinned
+    // mmc_freq_drain(): rows before a coordinate watermark leave while later batches are still being copied and decoded
+    std::vector<uint32_t> drained_to;                              // per contig: positions below this were returned by a drain
+    uint32_t wm_tid = 0, wm_pos = 0; bool wm_set = false;          // watermark of the last drain that returned rows
+    bool drain_violated = false;                                   // a batch uploaded after a drain starts before its watermark
+    mmc_freq_rec_t *h_drain[2] = {nullptr, nullptr}; size_t h_drain_cap[2] = {0, 0}; int drain_flip = 0;   // pinned, alternating
     unsigned long long *h_totals = nullptr;                        // pinned, fin_jobs_cap entries
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
     // results
@@ -274,8 +280,10 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
     uint64_t pool_need = 0;                    // split path: words of scratch for every read's dir | cq | cr
     std::vector<uint32_t> &need = ctx->need_tmp;   // per read: arena words for un-sampled CIGAR arrays + rank index
     need.resize(n);
+    uint64_t first = ~0ull;                    // (tid, pos) as one key; tid < 0 sorts last
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t L = b.l_seq[i], nc = b.n_cigar[i];
+        first = std::min(first, ((uint64_t)(uint32_t)b.tid[i] << 32) | (uint32_t)std::max<int32_t>(0, b.pos[i]));
         max_cig = std::max(max_cig, nc); max_l = std::max(max_l, L);
         const uint64_t n_u4 = ((uint64_t)L + 31) >> 5;
         pool_need += 164 + 2ull * nc + 8;
@@ -291,6 +299,8 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
         while (mb > 1 && (ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed)) / 4u < p95) --mb;
     }
     s.max_cig = max_cig; s.max_l = max_l; s.pool_need = pool_need; s.variant = mb;
+    s.min_tid = (uint32_t)(first >> 32); s.min_pos = (uint32_t)first;
+    if (n && ctx->wm_set && first < (((uint64_t)ctx->wm_tid << 32) | ctx->wm_pos)) ctx->drain_violated = true;   // see mmc_freq_drain()
     // Two implementations of the stage: k_decode_warp<MINB,PRE> keeps a read's rank index and CIGAR arrays in its arena -- fewest
     // instructions while three CTAs fit an SM (HiFi: 15 kb reads, ~30 CIGAR ops) -- and k_decode_stream needs constant shared
     // memory per warp whatever the read (ONT CIGARs, 50 kb reads: 24 warps per SM where the former drops to 16 or 8).
@@ -814,6 +824,7 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (ctx->d_sn_rows) cudaFree(ctx->d_sn_rows);
     if (ctx->h_sn_rows) cudaFreeHost(ctx->h_sn_rows);
     if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
+    for (int k = 0; k < 2; ++k) if (ctx->h_drain[k]) cudaFreeHost(ctx->h_drain[k]);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     if (ctx->ev_d0) cudaEventDestroy(ctx->ev_d0);
     if (ctx->ev_d1) cudaEventDestroy(ctx->ev_d1);
@@ -1106,20 +1117,30 @@ static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn) {
     return MMC_OK;
 }
 
-extern "C" {
-
-int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
-    MMC_DEV(ctx);
-    if (!ctx || !recs || !n_recs) return MMC_EINVAL;
-    if (ctx->opts.subtool != MMC_FREQ) return fail(ctx, MMC_ESTATE, "mmc_freq_finalize: context was created for view");
-    int rc = mmc_sync(ctx);
+// The rows of the count cells in coordinate order.  drain == false: everything no drain has returned yet (after waiting
+// for every batch).  drain == true: what lies before the watermark (wm_tid, wm_pos), after waiting only for the batches
+// that hold a read starting before it -- later batches keep copying and decoding while these rows are compacted and read
+// back (they only touch cells at or after the watermark).
+static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_pos, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
+    int rc = MMC_OK;
+    const uint64_t wm_key = ((uint64_t)wm_tid << 32) | wm_pos;
+    if (!drain) rc = mmc_sync(ctx);
+    else for (Slot &s : ctx->slots) {
+        if (!s.in_flight || ((((uint64_t)s.min_tid << 32) | s.min_pos) >= wm_key && s.n_reads_submitted)) continue;
+        const int r1 = wait_slot(ctx, s);
+        if (r1 != MMC_OK && rc == MMC_OK) rc = r1;
+    }
     if (rc != MMC_OK) return rc;
+    *n_recs = 0; *recs = nullptr;
     rc = refresh_code_names(ctx);
     if (rc != MMC_OK) return rc;
     const size_t nc = ctx->contigs.size();
+    if (ctx->drained_to.size() != nc) ctx->drained_to.assign(nc, 0u);
     std::vector<int32_t> touch(2 * std::max<size_t>(1, nc));
     if (nc) CU(ctx, cudaMemcpy(touch.data(), ctx->d_touch, sizeof(int32_t) * 2 * nc, cudaMemcpyDeviceToHost));
     const uint32_t spp = 2u * (uint32_t)ctx->n_code_slots * (uint32_t)ctx->n_hap_slots;
+    mmc_freq_rec_t *&h_rows = drain ? ctx->h_drain[ctx->drain_flip] : ctx->h_rows;
+    size_t &h_rows_cap = drain ? ctx->h_drain_cap[ctx->drain_flip] : ctx->h_rows_cap;
 
     struct Job { int32_t tid; int32_t lo; uint64_t n_cells; uint64_t n_tiles; uint64_t tile0; };
     std::vector<Job> jobs;
@@ -1127,6 +1148,11 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
     for (size_t i = 0; i < nc; ++i) {
         if (!ctx->contigs[i].loaded) continue;
         int32_t lo = touch[i], hi = touch[nc + i];
+        if ((int64_t)ctx->drained_to[i] > lo) lo = (int32_t)std::min<uint32_t>(ctx->drained_to[i], (uint32_t)INT32_MAX);
+        if (drain) {
+            if ((uint32_t)i > wm_tid) break;
+            if ((uint32_t)i == wm_tid && (int64_t)wm_pos < hi) hi = (int32_t)wm_pos;
+        }
         if (lo >= hi) continue;
         Job j; j.tid = (int32_t)i; j.lo = lo; j.n_cells = (uint64_t)(hi - lo) * spp;
         j.n_tiles = (j.n_cells + kTileCells - 1) / kTileCells; j.tile0 = tiles;
@@ -1139,6 +1165,7 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
     if (sn > ctx->sparse_cap)
         return fail(ctx, MMC_ENOMEM, "sparse count buffer overflow (%llu records > capacity %llu); raise sparse_capacity",
                     sn, (unsigned long long)ctx->sparse_cap);
+    if (drain && sn > 0) return MMC_OK;        // records of the side buffer are not partitioned by position: left to mmc_freq_finalize()
     const bool dev_sparse = sn > 0 && sn >= ctx->sparse_dev_min && sn < 0x7fffffffull;   // many records (--insertions): sorted on the device
     std::vector<SparseRec> raw(dev_sparse ? 0 : sn);
     if (sn && !dev_sparse) {
@@ -1146,12 +1173,12 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
         ctx->tm.d2h_bytes += sizeof(SparseRec) * sn;
     }
     auto ensure_rows = [&](uint64_t rows) -> int {           // pinned result buffer: dense rows + room to merge the sparse ones in
-        if (rows <= ctx->h_rows_cap) return MMC_OK;
-        if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
-        ctx->h_rows = nullptr; ctx->h_rows_cap = 0;
+        if (rows <= h_rows_cap) return MMC_OK;
+        if (h_rows) cudaFreeHost(h_rows);
+        h_rows = nullptr; h_rows_cap = 0;
         const size_t cap = rows + rows / 8 + 1024;
-        CU(ctx, cudaMallocHost((void **)&ctx->h_rows, sizeof(mmc_freq_rec_t) * cap));
-        ctx->h_rows_cap = cap;
+        CU(ctx, cudaMallocHost((void **)&h_rows, sizeof(mmc_freq_rec_t) * cap));
+        h_rows_cap = cap;
         return MMC_OK;
     };
     uint64_t n_dense = 0;
@@ -1255,7 +1282,7 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             rc = ensure_rows(n_dev_rows + (dev_sparse ? 0 : sn));
             if (rc != MMC_OK) return rc;
             CU(ctx, cudaEventRecord(ctx->ev_d0, ctx->fin_stream));
-            CU(ctx, cudaMemcpyAsync(ctx->h_rows, src, sizeof(FreqRecDev) * n_dev_rows, cudaMemcpyDeviceToHost, ctx->fin_stream));
+            CU(ctx, cudaMemcpyAsync(h_rows, src, sizeof(FreqRecDev) * n_dev_rows, cudaMemcpyDeviceToHost, ctx->fin_stream));
             CU(ctx, cudaEventRecord(ctx->ev_d1, ctx->fin_stream));
             ctx->tm.d2h_bytes += sizeof(FreqRecDev) * n_dev_rows;
         }
@@ -1313,7 +1340,7 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
             if (x.ins_offset != y.ins_offset) return x.ins_offset < y.ins_offset;
             return x.hap < y.hap;
         };
-        mmc_freq_rec_t *rows = ctx->h_rows;
+        mmc_freq_rec_t *rows = h_rows;
         size_t end = n_dense;                                // dense rows [0, end) are still where the copy put them
         for (size_t j = ns; j-- > 0;) {
             const mmc_freq_rec_t &sr = sparse[j];
@@ -1335,7 +1362,44 @@ int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_rec
                 (unsigned long long)n_dense, dev_sparse ? "dense + sparse, merged there" : "dense", sn, ns, ms(t_s0, t_s1), ms(t_s1, t_s2), ms(t_s2, t_s3));
     }
     *n_recs = n_dense + ns;
-    *recs = *n_recs ? ctx->h_rows : nullptr;
+    *recs = *n_recs ? h_rows : nullptr;
+    if (drain) {                                              // what this call returned is never returned again
+        for (size_t i = 0; i < nc && (uint32_t)i <= wm_tid; ++i)
+            ctx->drained_to[i] = std::max(ctx->drained_to[i], (uint32_t)i < wm_tid ? ctx->contigs[i].len : std::min(wm_pos, ctx->contigs[i].len));
+        if (!ctx->wm_set || wm_key > (((uint64_t)ctx->wm_tid << 32) | ctx->wm_pos)) { ctx->wm_tid = wm_tid; ctx->wm_pos = wm_pos; }
+        ctx->wm_set = true;
+        ctx->drain_flip ^= 1;
+    }
+    return MMC_OK;
+}
+
+extern "C" {
+
+int mmc_freq_finalize(mmc_ctx *ctx, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
+    MMC_DEV(ctx);
+    if (!ctx || !recs || !n_recs) return MMC_EINVAL;
+    if (ctx->opts.subtool != MMC_FREQ) return fail(ctx, MMC_ESTATE, "mmc_freq_finalize: context was created for view");
+    if (ctx->drain_violated)
+        return fail(ctx, MMC_EORDER, "a batch submitted after mmc_freq_drain() holds a read that starts before the drained watermark "
+                                     "(input not coordinate-sorted): call mmc_freq_undrain(), drop the drained rows and finalize again");
+    return finalize_rows(ctx, false, 0, 0, recs, n_recs);
+}
+
+int mmc_freq_drain(mmc_ctx *ctx, int32_t tid, uint32_t pos, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
+    MMC_DEV(ctx);
+    if (!ctx || !recs || !n_recs || tid < 0) return MMC_EINVAL;
+    if (ctx->opts.subtool != MMC_FREQ) return fail(ctx, MMC_ESTATE, "mmc_freq_drain: context was created for view");
+    *recs = nullptr; *n_recs = 0;
+    if (ctx->drain_violated) return MMC_OK;                   // nothing more leaves early; mmc_freq_finalize() reports it
+    if (ctx->wm_set && (((uint64_t)(uint32_t)tid << 32) | pos) <= (((uint64_t)ctx->wm_tid << 32) | ctx->wm_pos)) return MMC_OK;
+    return finalize_rows(ctx, true, (uint32_t)tid, pos, recs, n_recs);
+}
+
+int mmc_freq_undrain(mmc_ctx *ctx) {
+    MMC_DEV(ctx);
+    if (!ctx) return MMC_EINVAL;
+    ctx->drained_to.assign(ctx->contigs.size(), 0u);
+    ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false;
     return MMC_OK;
 }
 
@@ -1359,6 +1423,8 @@ int mmc_freq_reset(mmc_ctx *ctx) {
     CU(ctx, cudaMemsetAsync(ctx->d_sparse_n, 0, 8, ctx->fin_stream));
     CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
     ctx->sparse_seen = 0;
+    ctx->drained_to.assign(nc, 0u);
+    ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false;
     return MMC_OK;
 }
 

@@ -15,6 +15,9 @@ void print_view_header(FILE *fp, const OutOpts &o);
 // recs sorted by (tid,pos,...) as mmc_freq_finalize() returns them; code_names[code] gives the string
 void print_freq_records(FILE *fp, const OutOpts &o, const std::vector<std::string> &contig_names,
                         const mmc_freq_rec_t *recs, uint64_t n, const std::vector<std::string> &code_names);
+// rows [b,e) of one contig (all of tid == that contig) appended to *out as text: what print_freq_records() writes for them
+void format_freq_rows(std::string *out, const OutOpts &o, const std::string &contig_name, const mmc_freq_rec_t *recs, uint64_t b, uint64_t e,
+                      const std::vector<std::string> &code_names);
 void print_view_records(FILE *fp, const OutOpts &o, const std::vector<std::string> &contig_names,
                         const mmc_batch_t *batch, const BatchMeta &meta,
                         const mmc_view_rec_t *recs, uint64_t n, const std::vector<std::string> &code_names);

@@ -14,7 +14,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -323,6 +326,56 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         ERROR("%s", msg.c_str());
         exit(EXIT_FAILURE);
     };
+    // ---- freq: rows of finished positions leave the device while the BAM is still being read (mmc_freq_drain: the reads of a
+    // coordinate-sorted BAM never come back to positions before a batch's first read) and are turned into text by a worker
+    // thread, per contig; at the end the contigs are written in strcmp order (cmp_key_fast, src/mod.c:59-87).  Anything else
+    // (--shard-regions, a BAM that turns out not to be sorted) is read back and formatted after the last batch as before.
+    const bool stream_rows = subtool == MMC_FREQ && big_tid < 0 && !getenv("MINIMOD_NO_DRAIN");
+    struct FmtJob { std::vector<mmc_freq_rec_t> rows; std::vector<std::string> codes; };
+    std::vector<std::string> contig_text(stream_rows ? n_contigs : 0);
+    std::deque<FmtJob> fmt_queue;
+    std::mutex fmt_mu;
+    std::condition_variable fmt_cv;
+    bool fmt_done = false;
+    uint64_t rows_early = 0, rows_total = 0;
+    double fmt_secs = 0;
+    std::thread fmt_thread;
+    if (stream_rows) fmt_thread = std::thread([&]() {
+        for (;;) {
+            FmtJob job;
+            {
+                std::unique_lock<std::mutex> lk(fmt_mu);
+                fmt_cv.wait(lk, [&]() { return fmt_done || !fmt_queue.empty(); });
+                if (fmt_queue.empty()) return;
+                job = std::move(fmt_queue.front());
+                fmt_queue.pop_front();
+            }
+            const double t0 = realtime();
+            const uint64_t n = job.rows.size();
+            for (uint64_t i = 0; i < n;) {
+                uint64_t j = i;
+                while (j < n && job.rows[j].tid == job.rows[i].tid) ++j;
+                format_freq_rows(&contig_text[job.rows[i].tid], oo, bam.names[job.rows[i].tid], job.rows.data(), i, j, job.codes);
+                i = j;
+            }
+            fmt_secs += realtime() - t0;
+        }
+    });
+    auto fmt_push = [&](mmc_ctx *c, const mmc_freq_rec_t *r, uint64_t n) {
+        if (!n) return;
+        FmtJob job;
+        job.rows.assign(r, r + n);                        // out of the library's alternating pinned buffers
+        job.codes = code_names_of(c);
+        { std::lock_guard<std::mutex> lk(fmt_mu); fmt_queue.push_back(std::move(job)); }
+        fmt_cv.notify_one();
+    };
+    auto fmt_idle = [&]() {                               // every queued job formatted
+        for (;;) {
+            { std::lock_guard<std::mutex> lk(fmt_mu); if (fmt_queue.empty()) break; }
+            std::this_thread::yield();
+        }
+    };
+
     int more = 1;
     while (more) {
         int d = 0;
@@ -349,6 +402,17 @@ static int run_tool(int subtool, int argc, char *argv[]) {
                 cputime() / (realtime() - realtime0), st.n_recs, st.processed_bytes / (1000.0 * 1000.0));
         if (mmc_batch_submit(c, b) != MMC_OK) { ERROR("%s", mmc_strerror(c)); exit(EXIT_FAILURE); }
         rg.b[si] = b;
+        if (stream_rows && b->n_reads && b->tid[0] >= 0) {
+            // the batches submitted before this one hold every read that starts before its first read
+            for (int i = 1; i < n_slots; ++i) {
+                const int oi = (si + i) % n_slots;
+                if (rg.b[oi] && mmc_batch_wait(c, rg.b[oi]) != MMC_OK) die_read(c, rg.meta[oi]);
+            }
+            const mmc_freq_rec_t *recs = nullptr; uint64_t n = 0;
+            if (mmc_freq_drain(c, b->tid[0], (uint32_t)std::max<int32_t>(0, b->pos[0]), &recs, &n) != MMC_OK) { ERROR("%s", mmc_strerror(c)); exit(EXIT_FAILURE); }
+            rows_early += n; rows_total += n;
+            fmt_push(c, recs, n);
+        }
         if (subtool == MMC_VIEW) {
             const mmc_view_rec_t *recs = nullptr; uint64_t n = 0;
             if (mmc_view_fetch(c, b, &recs, &n) != MMC_OK) die_read(c, rg.meta[si]);
@@ -375,7 +439,37 @@ static int run_tool(int subtool, int argc, char *argv[]) {
 
     double sort_time = 0, halo_ms = 0;
     uint64_t halo_bytes = 0;
-    if (subtool == MMC_FREQ) {
+    if (stream_rows) {
+        double s0 = realtime();
+        for (int d = 0; d < ndev; ++d) {
+            const mmc_freq_rec_t *recs = nullptr; uint64_t n = 0;
+            int rc = mmc_freq_finalize(ctxs[d], &recs, &n);
+            if (rc == MMC_EORDER) {
+                // the BAM was not coordinate-sorted after all: nothing is lost (drains never clear counts), the rows this
+                // device handed out early are dropped and its whole table is read back
+                WARNING("%s", "reads are not in coordinate order: the rows written out early are discarded and the table is rebuilt at the end");
+                fmt_idle();
+                { std::lock_guard<std::mutex> lk(fmt_mu); }
+                for (int t = 0; t < n_contigs; ++t) if (owner[t] == d) std::string().swap(contig_text[t]);
+                rows_total = 0; rows_early = 0;           // (reported figures only)
+                if (mmc_freq_undrain(ctxs[d]) != MMC_OK) { ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE); }
+                rc = mmc_freq_finalize(ctxs[d], &recs, &n);
+            }
+            if (rc != MMC_OK) { ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE); }
+            rows_total += n;
+            fmt_push(ctxs[d], recs, n);
+        }
+        sort_time = realtime() - s0;
+        double o0 = realtime();
+        { std::lock_guard<std::mutex> lk(fmt_mu); fmt_done = true; }
+        fmt_cv.notify_all();
+        fmt_thread.join();
+        std::vector<int> order(n_contigs);
+        for (int i = 0; i < n_contigs; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return strcmp(bam.names[a].c_str(), bam.names[b].c_str()) < 0; });
+        for (int t : order) if (!contig_text[t].empty()) fwrite(contig_text[t].data(), 1, contig_text[t].size(), opt.out);
+        output_time += realtime() - o0;
+    } else if (subtool == MMC_FREQ) {
         double s0 = realtime();
         if (big_tid >= 0 && mmc_region_reduce(ctxs.data(), ndev, big_tid, &halo_ms, &halo_bytes) != MMC_OK) {
             ERROR("%s", mmc_strerror(ctxs[0])); exit(EXIT_FAILURE);
@@ -456,6 +550,8 @@ static int run_tool(int subtool, int argc, char *argv[]) {
     fprintf(stderr, "\n[%s] Data output time: %.3f sec", func, output_time);
     fprintf(stderr, "\n[%s] Device: H2D %.3f sec (%.1f MB), %lu kernel launches", func, tm.h2d_ms / 1e3, tm.h2d_bytes / 1e6,
             (unsigned long)tm.kernel_launches);
+    if (stream_rows) fprintf(stderr, "\n[%s] Rows: %lu, of which %lu left the device and were formatted while the BAM was being read (%.3f sec of formatting on a worker thread)",
+                             func, (unsigned long)rows_total, (unsigned long)rows_early, fmt_secs);
     if (ndev > 1) fprintf(stderr, "\n[%s] Devices: %d (%s); boundary reduce %.3f ms, %.1f MB", func, ndev,
                           big_tid >= 0 ? "longest contig cut by read start, the others dealt by length" : "contigs dealt by length", halo_ms, halo_bytes / 1e6);
     fprintf(stderr, "\n");

@@ -132,3 +132,50 @@ def test_sparse_side_buffer_grows(cli, tmp_path):
     mine = run(cli, ["freq"] + cli_args(3) + ["-K", "11", "--sparse-cap", "64", fa, bam]).stdout
     want = run(REF_BIN, ["freq"] + cli_args(3) + ["-t", "4", fa, bam]).stdout
     assert sorted_lines(mine) == sorted_lines(want) and len(mine.splitlines()) > 5000
+
+
+@needs_ref
+@pytest.mark.parametrize("cli", CLIS)
+def test_rows_leave_early_and_the_text_is_identical(cli, tmp_path):
+    """Coordinate-sorted, several contigs (names out of strcmp order), many small batches: most rows are drained and formatted
+    while the BAM is still being read (mmc_freq_drain); the output is byte-identical to the reference's."""
+    s = Synth(2, contigs=(("zeta", 200000), ("alpha", 120000), ("chrM", 16569), ("beta", 90000)), coverage=3.0)
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "reads.bam")
+    s.write_fasta(fa); s.write_bam(bam); s.close()
+    r = run(cli, ["freq"] + cli_args(2) + ["-K", "9", fa, bam])
+    want = run(REF_BIN, ["freq"] + cli_args(2) + ["-t", "4", fa, bam]).stdout
+    assert r.stdout == want and len(want.splitlines()) > 3000
+    line = [l for l in r.stderr.decode().splitlines() if "left the device" in l][0]
+    total, early = int(line.split("Rows: ")[1].split(",")[0]), int(line.split("of which ")[1].split()[0])
+    assert total == len(want.splitlines()) and early > total // 2, line
+    env = dict(os.environ, MINIMOD_NO_DRAIN="1")
+    plain = subprocess.run([cli, "freq"] + cli_args(2) + ["-K", "9", fa, bam], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert plain.returncode == 0 and plain.stdout == want
+
+
+@needs_ref
+@pytest.mark.parametrize("cli", CLIS)
+def test_unsorted_bam_falls_back_to_one_read_back(cli, tmp_path):
+    """Reads out of coordinate order (the header even claims SO:coordinate): rows drained early are dropped, the table is
+    rebuilt at the end, the output equals the reference's."""
+    import random
+    rnd = random.Random(7)
+    ref = "".join(rnd.choice("ACGT") for _ in range(6000))
+    fa, bam = str(tmp_path / "r.fa"), str(tmp_path / "r.bam")
+    with open(fa, "w") as fh:
+        fh.write(">c1\n" + ref + "\n>c0\n" + ref[::-1] + "\n")
+    recs = []
+    for i in range(60):
+        tid = i % 2
+        src = ref if tid == 0 else ref[::-1]
+        pos = rnd.randrange(0, 5000)
+        seq = src[pos:pos + 400]
+        ncs = seq.count("C")
+        k = min(ncs, 12)
+        recs.append(dict(tid=tid, pos=pos, flag=0, qname=f"r{i}", cigar=[("M", 400)], seq=seq,
+                         aux=mm_ml("C+m?," + ",".join("1" for _ in range(k)) + ";", [rnd.choice((5, 250)) for _ in range(k)])))
+    write_bam(bam, [("c1", len(ref)), ("c0", len(ref))], recs)
+    r = run(cli, ["freq", "-c", "m[*]", "-K", "4", fa, bam])
+    want = run(REF_BIN, ["freq", "-c", "m[*]", "-t", "2", fa, bam]).stdout
+    assert sorted_lines(r.stdout) == sorted_lines(want) and len(want.splitlines()) > 200
+    assert b"not in coordinate order" in r.stderr
