@@ -367,19 +367,31 @@ def measure(env, config, synth, steps, warmup, first=0, count=None, shard_note=N
     # decoded: mmc_freq_drain() compacts and reads them back while the later batches are still crossing PCIe the other way
     lag = max(1, args.drain_lag)
     marks = [(int(b.contents.tid[0]), int(b.contents.pos[0])) if b.contents.n_reads else None for b in held]
-    use_drain = not args.no_drain and halo is None
+    use_drain = not args.no_drain and not os.environ.get("BENCH_NO_DRAIN") and halo is None
+
+    trace = [] if os.environ.get("BENCH_TRACE") else None
 
     def e2e_step(collect=None):
+        t_a = time.time()
         env.chk(ctxB, lib.mmc_freq_reset(ctxB))
+        if trace is not None:
+            trace.append(("reset", 0, time.time() - t_a, 0))
         total = 0
         for k, b in enumerate(held):
+            t_a = time.time()
             env.chk(ctxB, lib.mmc_batch_submit(ctxB, b))            # async H2D + kernels on the slot's stream
+            t_b = time.time()
             if use_drain and k >= lag and marks[k - lag + 1] is not None:
                 env.chk(ctxB, lib.mmc_freq_drain(ctxB, marks[k - lag + 1][0], marks[k - lag + 1][1], C.byref(recs), C.byref(nrec)))
                 total += int(nrec.value)
                 if collect is not None and nrec.value:
                     collect(recs, int(nrec.value))
+            if trace is not None:
+                trace.append(("submit+drain", k, t_b - t_a, time.time() - t_b))
+        t_a = time.time()
         env.chk(ctxB, lib.mmc_freq_finalize(ctxB, C.byref(recs), C.byref(nrec)))   # waits, compacts, D2H of the remaining rows
+        if trace is not None:
+            trace.append(("finalize", 0, time.time() - t_a, 0))
         if collect is not None and nrec.value:
             collect(recs, int(nrec.value))
         return total + int(nrec.value)
@@ -409,6 +421,9 @@ def measure(env, config, synth, steps, warmup, first=0, count=None, shard_note=N
     if halo is None:
         assert rows_e2e == n_rows, (rows_e2e, n_rows)
     e2e_wall = te1 - te0
+    if trace is not None and env.rank == 0:
+        for what, k, a, b in trace[-(len(held) + 2):]:
+            print(f"[e2e trace] {what} {k}: {1e3 * a:.2f} ms, {1e3 * b:.2f} ms", file=sys.stderr)
     for b in held:
         lib.mmc_batch_release(ctxB, b)
     lib.mmc_destroy(ctxB)
@@ -441,7 +456,7 @@ def measure(env, config, synth, steps, warmup, first=0, count=None, shard_note=N
                    "emitted_updates_this_rank": emitted,
                    "l2": "inputs (%.2f GB per pass on this rank) exceed the 126 MB L2" % (alg_bytes / 1e9),
                    "gen_s": gen_s, "e2e_chunks": chunks, "e2e_steps": e2e_steps,
-                   "e2e_read_back": (f"mmc_freq_drain after each batch (watermark = first read of the batch submitted {lag - 1} earlier), "
+                   "e2e_read_back": (f"mmc_freq_drain after each batch submit (watermark = first read of the batch submitted {lag - 1} before it), "
                                      "remainder by mmc_freq_finalize; row count and checksum equal to the single-finalize table") if use_drain
                                     else "one mmc_freq_finalize after the last batch",
                    "seq_transport": "2 bits per base + exception list in the pinned host buffers, expanded to BAM's 4-bit form on upload "
@@ -492,7 +507,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=8, help="batches per job on the e2e path")
     ap.add_argument("--seq-packing", type=int, default=2, choices=(2, 4), help="bits per base of SEQ in the host buffers (2: + exception list, expanded on the device)")
     ap.add_argument("--no-drain", action="store_true", help="e2e: read all rows back after the last batch instead of draining finished positions early")
-    ap.add_argument("--drain-lag", type=int, default=2, help="e2e: batches kept in flight behind the drain watermark")
+    ap.add_argument("--drain-lag", type=int, default=1, help="e2e: batches kept in flight behind the drain watermark")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", action="store_true", help="only the headline workload: no per-config sub-results / region-sharding leg")
     args = ap.parse_args()

@@ -135,6 +135,8 @@ struct mmc_ctx {
     std::vector<uint32_t> drained_to;                              // per contig: positions below this were returned by a drain
     uint32_t wm_tid = 0, wm_pos = 0; bool wm_set = false;          // watermark of the last drain that returned rows
     bool drain_violated = false;                                   // a batch uploaded after a drain starts before its watermark
+    cudaEvent_t ev_reset = nullptr; bool reset_pending = false;    // mmc_freq_reset() clears on fin_stream; the next decode launches wait for it on the device
+    std::vector<int32_t> reset_touch;                              // (source of its asynchronous copy)
     mmc_freq_rec_t *h_drain[2] = {nullptr, nullptr}; size_t h_drain_cap[2] = {0, 0}; int drain_flip = 0;   // pinned, alternating
     unsigned long long *h_totals = nullptr;                        // pinned, fin_jobs_cap entries
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
@@ -203,6 +205,14 @@ const char *read_error_text(uint32_t code) {
     case kErrSeqTooLong: return "read longer than 2^28 bases (library limit)";
     default: return "unknown per-read error";
     }
+}
+
+// host-side reads and writes of the count state (touch ranges, side-buffer fill level, cells) come after a pending reset
+int reset_settle(mmc_ctx *ctx) {
+    if (!ctx->reset_pending) return MMC_OK;
+    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    ctx->reset_pending = false;
+    return MMC_OK;
 }
 
 int setup_slot(mmc_ctx *ctx, Slot &s) {
@@ -396,6 +406,7 @@ int reserve_sparse(mmc_ctx *ctx, const Slot &s) {
         return fail(ctx, MMC_ENOMEM, "cannot grow the sparse count buffer to %llu records (%.1f GB)", (unsigned long long)cap, cap * 16 / 1e9);
     }
     unsigned long long sn = 0;
+    { int rc = reset_settle(ctx); if (rc != MMC_OK) return rc; }
     CU(ctx, cudaMemcpy(&sn, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost));
     if (sn > ctx->sparse_cap) sn = ctx->sparse_cap;
     if (sn) CU(ctx, cudaMemcpy(nb, ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToDevice));
@@ -411,6 +422,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     // reset the slot's device state: err = ~0, view_n = 0, work counters and deferred count = 0
     // layout: u64 [0] err, [1] view_n, [4] pool cursor; u32 [4] work counter of k_decode_warp, [5] reads it defers,
     // [6] work counter of k_decode, [7] reads the flat path defers, [10] tiles, [11] reads with '.' blocks
+    if (ctx->reset_pending) CU(ctx, cudaStreamWaitEvent(s.stream, ctx->ev_reset, 0));   // the counts are being cleared: copies may overlap that, kernels may not
     memset(s.h_state, 0, 64);
     s.h_state[0] = ~0ull;
     CU(ctx, cudaMemcpyAsync(s.d_state, s.h_state, 64, cudaMemcpyHostToDevice, s.stream));
@@ -613,6 +625,12 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     if (opts->subtool != MMC_FREQ && opts->subtool != MMC_VIEW) return fail(nullptr, MMC_EINVAL, "mmc_create: subtool must be MMC_FREQ or MMC_VIEW");
     if (opts->n_mods < 1 || opts->n_mods > MMC_MAX_MODS || !opts->mods) return fail(nullptr, MMC_EINVAL, "mmc_create: need 1..%d modification codes", MMC_MAX_MODS);
     if (n_contigs < 0 || (n_contigs > 0 && (!names || !lens))) return fail(nullptr, MMC_EINVAL, "mmc_create: bad contig table");
+    // MMC_TRACE_CREATE=1: where the start-up time goes (stderr)
+    const bool tr = getenv("MMC_TRACE_CREATE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) {
+        if (tr) fprintf(stderr, "[mmc_create] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(), what);
+    };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(nullptr, MMC_ECUDA, "mmc_create: no CUDA device available (libminimod_cuda has no CPU fallback)");
@@ -664,7 +682,10 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         }                                                                                                    \
     } while (0)
 
+    stamp("driver initialised (cudaGetDeviceCount)");
     CUC(cudaSetDevice(o.device));
+    CUC(cudaFree(nullptr));
+    stamp("device context created");
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, o.device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -693,6 +714,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
 #undef MMC_WARP_ATTR
     }
 
+    stamp("kernel attributes set (modules loaded)");
     // ---- -c entries -> device tables
     std::vector<ReqMod> req(o.n_mods);
     ctx->wild_req = -1;
@@ -757,12 +779,15 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     CUC(cudaStreamCreateWithFlags(&ctx->fin_stream, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&ctx->ev_f0)); CUC(cudaEventCreate(&ctx->ev_f1));
     CUC(cudaEventCreate(&ctx->ev_d0)); CUC(cudaEventCreate(&ctx->ev_d1));
+    CUC(cudaEventCreate(&ctx->ev_reset));
 
+    stamp("tables and side buffers allocated");
     ctx->slots.resize(o.n_slots);
     for (Slot &s : ctx->slots) {
         int rc = setup_slot(ctx, s);
         if (rc != MMC_OK) { g_create_error = ctx->err; mmc_destroy(ctx); return rc; }
     }
+    stamp("batch slots allocated (pinned host + device arenas)");
     // touch ranges start empty: [lo x n_contigs][hi x n_contigs]
     {
         const size_t m = (size_t)n_contigs;
@@ -828,6 +853,7 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     if (ctx->ev_d0) cudaEventDestroy(ctx->ev_d0);
     if (ctx->ev_d1) cudaEventDestroy(ctx->ev_d1);
+    if (ctx->ev_reset) cudaEventDestroy(ctx->ev_reset);
     if (ctx->ev_f0) cudaEventDestroy(ctx->ev_f0);
     if (ctx->ev_f1) cudaEventDestroy(ctx->ev_f1);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
@@ -996,7 +1022,7 @@ int mmc_batch_release(mmc_ctx *ctx, mmc_batch_t *batch) {
 int mmc_sync(mmc_ctx *ctx) {
     MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
-    int first = MMC_OK;
+    int first = reset_settle(ctx);
     for (Slot &s : ctx->slots) { int rc = wait_slot(ctx, s); if (rc != MMC_OK && first == MMC_OK) first = rc; }
     return first;
 }
@@ -1132,6 +1158,7 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
     }
     if (rc != MMC_OK) return rc;
     *n_recs = 0; *recs = nullptr;
+    if ((rc = reset_settle(ctx)) != MMC_OK) return rc;
     rc = refresh_code_names(ctx);
     if (rc != MMC_OK) return rc;
     const size_t nc = ctx->contigs.size();
@@ -1409,7 +1436,9 @@ int mmc_freq_reset(mmc_ctx *ctx) {
     int rc = mmc_sync(ctx);
     if (rc != MMC_OK) return rc;
     const size_t nc = ctx->contigs.size();
-    std::vector<int32_t> touch(2 * std::max<size_t>(1, nc));
+    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));         // (a previous reset's copy out of reset_touch)
+    std::vector<int32_t> &touch = ctx->reset_touch;
+    touch.assign(2 * std::max<size_t>(1, nc), 0);
     if (nc) CU(ctx, cudaMemcpy(touch.data(), ctx->d_touch, sizeof(int32_t) * 2 * nc, cudaMemcpyDeviceToHost));
     const size_t spp = 2 * (size_t)ctx->n_code_slots * ctx->n_hap_slots;
     for (size_t i = 0; i < nc; ++i) {
@@ -1421,7 +1450,10 @@ int mmc_freq_reset(mmc_ctx *ctx) {
     }
     if (nc) CU(ctx, cudaMemcpyAsync(ctx->d_touch, touch.data(), sizeof(int32_t) * 2 * nc, cudaMemcpyHostToDevice, ctx->fin_stream));
     CU(ctx, cudaMemsetAsync(ctx->d_sparse_n, 0, 8, ctx->fin_stream));
-    CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
+    // asynchronous: the next batches' H2D copies overlap the clearing; their kernels (launch_decode) and every later
+    // finalize / drain (same stream) are ordered behind it on the device
+    CU(ctx, cudaEventRecord(ctx->ev_reset, ctx->fin_stream));
+    ctx->reset_pending = true;
     ctx->sparse_seen = 0;
     ctx->drained_to.assign(nc, 0u);
     ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false;
@@ -1473,6 +1505,7 @@ int mmc_dense_slice(mmc_ctx *ctx, int32_t tid, uint32_t start, uint32_t end, voi
     if (tid < 0 || (size_t)tid >= ctx->contigs.size() || !ctx->contigs[tid].loaded || !ctx->contigs[tid].dev.cells)
         return fail(ctx, MMC_EINVAL, "mmc_dense_slice: contig %d has no dense counts", tid);
     if (start > end || end > ctx->contigs[tid].len) return fail(ctx, MMC_EINVAL, "mmc_dense_slice: bad range");
+    { MMC_DEV(ctx); int rc = reset_settle(ctx); if (rc != MMC_OK) return rc; }
     const size_t spp = 2 * (size_t)ctx->n_code_slots * ctx->n_hap_slots;
     *dev_ptr = ctx->contigs[tid].dev.cells + (size_t)start * spp;
     *n_cells = (uint64_t)(end - start) * spp;

@@ -1,0 +1,36 @@
+"""Parity at BASELINE.json's FULL sizes: the `minimod` binary on the full synthetic jobs of configs
+2, 3, 4 (chr22, 30x) and 5 (GRCh38-shaped 195 contigs, 1x), compared with the table the UNMODIFIED reference printed for
+the same deterministic files.  The reference ran where /root/reference exists (tools/make_fullsize_checksums.py) and only
+the order-independent digest of its output travels (tests/golden/fullsize_checksums.json)."""
+import os
+import shutil
+import tempfile
+
+import pytest
+
+import fullsize
+from helpers import ROOT
+
+CUDA_CLI = os.path.join(ROOT, "minimod_b200", "bin", "minimod")
+try:
+    SUMS = fullsize.load_checksums()
+except Exception:
+    SUMS = {}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", sorted(fullsize.JOBS))
+def test_full_size_table_equals_the_reference(config):
+    if config not in SUMS:
+        pytest.skip("no reference digest committed for this config (tools/make_fullsize_checksums.py)")
+    if os.environ.get("MINIMOD_FULLSIZE", "1") == "0":
+        pytest.skip("MINIMOD_FULLSIZE=0")
+    want = SUMS[config]
+    td = tempfile.mkdtemp(prefix="mm_full_")
+    try:
+        fa, bam, args, st = fullsize.write_job(config, td, threads=os.cpu_count() or 8)
+        assert int(st["n_reads"]) == want["reads"] and int(st["bases"]) == want["bases"]      # the same job as the reference saw
+        got, err = fullsize.digest_of_command([CUDA_CLI, "freq"] + args + ["-t", str(os.cpu_count() or 8), "-K", "4092", "-B", "100M", fa, bam])
+        assert (got["lines"], got["sum"], got["xor"]) == (want["lines"], want["sum"], want["xor"]), (got, want, err[-600:])
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
