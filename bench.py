@@ -257,6 +257,7 @@ def make_ctx(env, config, synth, n_slots, reads_cap, bases_cap):
     o.cap_ml_bytes = int(bases_cap * ratio[2]) + 16 * reads_cap
     o.sparse_capacity = 1 << 26
     o.seq_packing = env.args.seq_packing
+    o.cigar_packing = env.args.cigar_packing
     nc = len(synth.names)
     names = (C.c_char_p * max(1, nc))(*synth.names)
     lens = (C.c_uint32 * max(1, nc))(*synth.lens)
@@ -460,7 +461,9 @@ def measure(env, config, synth, steps, warmup, first=0, count=None, shard_note=N
                                      "remainder by mmc_freq_finalize; row count and checksum equal to the single-finalize table") if use_drain
                                     else "one mmc_freq_finalize after the last batch",
                    "seq_transport": "2 bits per base + exception list in the pinned host buffers, expanded to BAM's 4-bit form on upload "
-                                    "(inside e2e; `value` starts from the expanded, HBM-resident batch)" if args.seq_packing == 2 else "BAM 4-bit nibbles"},
+                                    "(inside e2e; `value` starts from the expanded, HBM-resident batch)" if args.seq_packing == 2 else "BAM 4-bit nibbles",
+                   "cigar_transport": "a byte per op + escape lists in the pinned host buffers, expanded to BAM's 32-bit words on upload (inside e2e)"
+                                      if args.cigar_packing == 8 else "BAM 32-bit words"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                      "kernel": "decode stage = " + desc + "; CUDA events on the launch stream bracket the whole stage (rank 0's shard)",
@@ -506,6 +509,7 @@ def main():
     ap.add_argument("--coverage", type=float, default=0.0, help="depth of the job (default: 2x for config 5, 30x for configs 2-4)")
     ap.add_argument("--chunks", type=int, default=8, help="batches per job on the e2e path")
     ap.add_argument("--seq-packing", type=int, default=2, choices=(2, 4), help="bits per base of SEQ in the host buffers (2: + exception list, expanded on the device)")
+    ap.add_argument("--cigar-packing", type=int, default=8, choices=(8, 32), help="CIGARs in the host buffers: a byte per op + escape lists (expanded on the device), or BAM's 32-bit words")
     ap.add_argument("--no-drain", action="store_true", help="e2e: read all rows back after the last batch instead of draining finished positions early")
     ap.add_argument("--drain-lag", type=int, default=1, help="e2e: batches kept in flight behind the drain watermark")
     ap.add_argument("--no-cpu-baseline", action="store_true")

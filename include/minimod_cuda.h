@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MMC_ABI_VERSION 1
+#define MMC_ABI_VERSION 2
 
 /* status codes */
 #define MMC_OK            0
@@ -101,7 +101,9 @@ typedef struct {
     int32_t  seq_packing;        /* how SEQ crosses PCIe: 0 or 4 -> BAM's 4-bit nibbles (batch->seq4);
                                     2 -> 2 bits per base + an exception list (batch->seq2 / seq_exc), expanded
                                     to the 4-bit form on the device.  SEQ is ~87 % of a batch's bytes. */
-    int32_t  reserved0;
+    int32_t  cigar_packing;      /* how CIGARs cross PCIe: 0 or 32 -> BAM's 32-bit words (batch->cigar); 8 -> the byte form
+                                    (batch->cig8), expanded to the words on the device.  ONT alignments have an op per
+                                    ~17 bases (a third of a whole-genome batch's bytes as words, ~1.2 bytes per op here). */
 } mmc_opts_t;
 
 /* A batch in flight.  Replaces the per-read fields of db_t (src/minimod.h:125-160) that
@@ -119,6 +121,12 @@ typedef struct {
  *                                             nibble of an odd-length read: (nibble index into the seq4 pool,
  *                                             i.e. 2*seq_off[i]+base) << 4 | BAM nt16 code (0 for the pad)
  * and still advances seq_used in seq4 bytes; the device rebuilds the identical 4-bit pool.
+ * With cigar_packing == 8 the packer writes, instead of cigar, one blob per read at cig8[cig8_off[i]] (16-byte aligned):
+ *   u32 n1                                    ops whose length does not fit the nibble
+ *   n_cigar[i] bytes, padded to 4             op | min(len,15) << 4             (15: the length is in the next list)
+ *   n1 bytes, padded to 4                     len - 15 if < 255, else 255       (255: the length is in the next list)
+ *   n2 x u32                                  len, for the ops marked 255, in op order
+ * and still sets cigar_off[i] / advances cigar_used in words; the device rebuilds the identical word pool.
  * Offsets are element indices into their pool (cigar: words; others: bytes); each must be a
  * multiple of MMC_ALIGN bytes, and every pool needs MMC_ALIGN bytes of slack after the last
  * slice (mmc_batch_acquire() sizes them so).  The host appends reads while
@@ -147,7 +155,9 @@ typedef struct {
     uint8_t  *seq2;                                     /* seq_packing == 2 only */
     uint64_t *seq_exc; uint64_t seq_exc_cap, seq_exc_used;
     uint32_t  seq_packing;                              /* 4 or 2: which of seq4 / seq2 the packer fills */
-    uint32_t  reserved0;
+    uint32_t  cigar_packing;                            /* 32 or 8: which of cigar / cig8 the packer fills */
+    uint8_t  *cig8;   uint64_t cig8_cap,  cig8_used;    /* cigar_packing == 8 only; in bytes */
+    uint64_t *cig8_off;
 } mmc_batch_t;
 
 /* One output row of `freq`: the decoded key + value of core->freq_map

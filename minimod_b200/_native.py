@@ -30,7 +30,7 @@ class MmcOpts(C.Structure):
                 ("max_bytes", C.c_uint64), ("sparse_capacity", C.c_uint64), ("dense_haps", C.c_int32),
                 ("dense_codes", C.c_int32), ("view_capacity", C.c_uint64),
                 ("cap_cigar_words", C.c_uint64), ("cap_seq_bytes", C.c_uint64), ("cap_mm_bytes", C.c_uint64),
-                ("cap_ml_bytes", C.c_uint64), ("seq_packing", C.c_int32), ("reserved0", C.c_int32)]
+                ("cap_ml_bytes", C.c_uint64), ("seq_packing", C.c_int32), ("cigar_packing", C.c_int32)]
 
 
 class MmcBatch(C.Structure):
@@ -47,7 +47,9 @@ class MmcBatch(C.Structure):
                 ("ml", C.POINTER(C.c_uint8)), ("ml_cap", C.c_uint64), ("ml_used", C.c_uint64),
                 ("priv", C.c_void_p),
                 ("seq2", C.POINTER(C.c_uint8)), ("seq_exc", C.POINTER(C.c_uint64)), ("seq_exc_cap", C.c_uint64),
-                ("seq_exc_used", C.c_uint64), ("seq_packing", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("seq_exc_used", C.c_uint64), ("seq_packing", C.c_uint32), ("cigar_packing", C.c_uint32),
+                ("cig8", C.POINTER(C.c_uint8)), ("cig8_cap", C.c_uint64), ("cig8_used", C.c_uint64),
+                ("cig8_off", C.POINTER(C.c_uint64))]
 
 
 class MmcFreqRec(C.Structure):

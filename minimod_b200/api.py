@@ -25,7 +25,7 @@ class MinimodError(RuntimeError):
 class Core:
     def __init__(self, subtool, bam, mod_codes="m", mod_thresh=None, insertions=False, haplotypes=False,
                  batch_size=512, max_bytes=20 * 1000 * 1000, allow_secondary=False, skip_supplementary=False,
-                 device=0, n_slots=3, dense_haps=0, dense_codes=0, sparse_capacity=0, seq_packing=2, lib=None):
+                 device=0, n_slots=3, dense_haps=0, dense_codes=0, sparse_capacity=0, seq_packing=2, cigar_packing=8, lib=None):
         self.lib = lib if lib is not None else N.load_cuda()
         self.host = N.load_host()
         self.subtool = N.MMC_FREQ if subtool in ("freq", N.MMC_FREQ) else N.MMC_VIEW
@@ -52,6 +52,7 @@ class Core:
         o.max_reads, o.max_bytes = batch_size, int(max_bytes)
         o.dense_haps, o.dense_codes, o.sparse_capacity = dense_haps, dense_codes, sparse_capacity
         o.seq_packing = seq_packing            # SEQ crosses PCIe at 2 bits per base (include/minimod_cuda.h); 4 = BAM nibbles
+        o.cigar_packing = cigar_packing        # CIGARs cross PCIe at a byte per op + escapes; 32 = BAM words
         names = (C.c_char_p * max(nt, 1))(*self.contig_names)
         lens = (C.c_uint32 * max(nt, 1))(*self.contig_lens)
         ctx = C.c_void_p()

@@ -50,6 +50,7 @@ struct Slot {
     size_t o_tid, o_pos, o_lseq, o_ncig, o_mmlen, o_mllen, o_cigoff, o_seqoff, o_mmoff, o_mloff, o_flag, o_hp;
     size_t o_cigar, o_seq, o_mm, o_ml;
     size_t o_seq2 = 0, o_exc = 0, cap_exc = 0;   // seq_packing == 2: transport form of SEQ; o_seq is then device-only (last in the arena)
+    size_t o_cig8 = 0, o_cig8off = 0;            // cigar_packing == 8: byte form of the CIGARs; o_cigar is then device-only
     size_t h_arena_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -92,6 +93,7 @@ struct mmc_ctx {
     std::string err, desc;
     int sm_count = 0, ctas_per_sm = 1, threads = 128;
     int seq_packing = 4;                                             // opts.seq_packing, or MMC_SEQ_PACKING
+    int cigar_packing = 32;                                          // opts.cigar_packing, or MMC_CIGAR_PACKING
     int stream_path = 1;                       // k_flat_setup + k_decode_stream (default): streaming merge, constant shared memory per warp
     uint32_t s_head = 256;                     // k_decode_stream: bytes of call LUTs in front of the arenas
     int s_minb = 6;                            // k_decode_stream<MINB>: resident CTAs per SM the registers are bounded for (MMC_STREAM_MINB)
@@ -231,8 +233,8 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     s.o_mmlen = take(R * 4); s.o_mllen = take(R * 4);
     s.o_cigoff = take(R * 8); s.o_seqoff = take(R * 8); s.o_mmoff = take(R * 8); s.o_mloff = take(R * 8);
     s.o_flag = take(R * 2); s.o_hp = take(R);
-    const bool two_bit = ctx->seq_packing == 2;
-    s.o_cigar = take(cap_cig + kSlack);
+    const bool two_bit = ctx->seq_packing == 2, cig_bytes = ctx->cigar_packing == 8;
+    if (!cig_bytes) s.o_cigar = take(cap_cig + kSlack);
     if (!two_bit) s.o_seq = take(cap_seq + kSlack);
     s.o_mm = take(cap_mm + kSlack); s.o_ml = take(cap_ml + kSlack);
     s.h_arena_bytes = off;
@@ -240,8 +242,13 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
         s.cap_exc = R + cap_seq / 64 + 1024;
         s.o_seq2 = take(cap_seq / 2 + kSlack); s.o_exc = take(8 * s.cap_exc);
         s.h_arena_bytes = off;
-        s.o_seq = take(cap_seq + kSlack);
     }
+    if (cig_bytes) {                                // a byte per op + escapes cross PCIe; the word pool exists on the device only
+        s.o_cig8off = take(R * 8); s.o_cig8 = take(cap_cig + kSlack);
+        s.h_arena_bytes = off;
+    }
+    if (two_bit) s.o_seq = take(cap_seq + kSlack);
+    if (cig_bytes) s.o_cigar = take(cap_cig + kSlack);
     s.arena_bytes = off;
     CU(ctx, cudaMallocHost((void **)&s.h_arena, s.h_arena_bytes));
     CU(ctx, cudaMalloc((void **)&s.d_arena, s.arena_bytes));
@@ -265,7 +272,9 @@ int setup_slot(mmc_ctx *ctx, Slot &s) {
     b.cigar_off = (uint64_t *)(h + s.o_cigoff); b.seq_off = (uint64_t *)(h + s.o_seqoff);
     b.mm_off = (uint64_t *)(h + s.o_mmoff); b.ml_off = (uint64_t *)(h + s.o_mloff);
     b.flag = (uint16_t *)(h + s.o_flag); b.hp = h + s.o_hp;
-    b.cigar = (uint32_t *)(h + s.o_cigar); b.cigar_cap = cap_cig / 4;
+    b.cigar = cig_bytes ? nullptr : (uint32_t *)(h + s.o_cigar); b.cigar_cap = cap_cig / 4;
+    b.cigar_packing = cig_bytes ? 8u : 32u;
+    if (cig_bytes) { b.cig8 = h + s.o_cig8; b.cig8_cap = cap_cig; b.cig8_off = (uint64_t *)(h + s.o_cig8off); }
     b.seq4 = two_bit ? nullptr : h + s.o_seq; b.seq_cap = cap_seq;
     b.seq_packing = two_bit ? 2u : 4u;
     if (two_bit) { b.seq2 = h + s.o_seq2; b.seq_exc = (uint64_t *)(h + s.o_exc); b.seq_exc_cap = s.cap_exc; }
@@ -340,9 +349,9 @@ int upload(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const size_t n = b.n_reads;
     if (n > b.max_reads || b.cigar_used > b.cigar_cap || b.seq_used > b.seq_cap || b.mm_used > b.mm_cap || b.ml_used > b.ml_cap ||
-        b.seq_exc_used > b.seq_exc_cap)
+        b.seq_exc_used > b.seq_exc_cap || b.cig8_used > b.cig8_cap)
         return fail(ctx, MMC_EINVAL, "batch exceeds its capacities");
-    const bool two_bit = ctx->seq_packing == 2;
+    const bool two_bit = ctx->seq_packing == 2, cig_bytes = ctx->cigar_packing == 8;
     uint64_t bytes = 0;
     CU(ctx, cudaEventRecord(s.ev_h0, s.stream));
     auto cp = [&](size_t off, size_t len) -> cudaError_t {
@@ -354,7 +363,16 @@ int upload(mmc_ctx *ctx, Slot &s) {
     CU(ctx, cp(s.o_mmlen, n * 4)); CU(ctx, cp(s.o_mllen, n * 4));
     CU(ctx, cp(s.o_cigoff, n * 8)); CU(ctx, cp(s.o_seqoff, n * 8)); CU(ctx, cp(s.o_mmoff, n * 8)); CU(ctx, cp(s.o_mloff, n * 8));
     CU(ctx, cp(s.o_flag, n * 2)); CU(ctx, cp(s.o_hp, n));
-    CU(ctx, cp(s.o_cigar, b.cigar_used * 4));
+    if (!cig_bytes) {
+        CU(ctx, cp(s.o_cigar, b.cigar_used * 4));
+    } else if (n) {                                             // transport form -> the word pool the kernels read
+        CU(ctx, cp(s.o_cig8off, n * 8)); CU(ctx, cp(s.o_cig8, b.cig8_used));
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
+        MMC_LAUNCH(k_unpack_cigar, grid, 256u, s.stream, (const uint8_t *)(s.d_arena + s.o_cig8), (const unsigned long long *)(s.d_arena + s.o_cig8off),
+                   (const uint32_t *)(s.d_arena + s.o_ncig), (const unsigned long long *)(s.d_arena + s.o_cigoff), (uint32_t)n, (uint32_t *)(s.d_arena + s.o_cigar));
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 1;
+    }
     CU(ctx, cp(s.o_mm, b.mm_used)); CU(ctx, cp(s.o_ml, b.ml_used));
     if (!two_bit) {
         CU(ctx, cp(s.o_seq, b.seq_used));
@@ -662,6 +680,8 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
     ctx->seq_packing = opts->seq_packing == 2 ? 2 : 4;
     if (const char *e = getenv("MMC_SEQ_PACKING")) { int v = atoi(e); if (v == 2 || v == 4) ctx->seq_packing = v; }   // test hook
+    ctx->cigar_packing = opts->cigar_packing == 8 ? 8 : 32;
+    if (const char *e = getenv("MMC_CIGAR_PACKING")) { int v = atoi(e); if (v == 8 || v == 32) ctx->cigar_packing = v; }   // test hook
     if (const char *e = getenv("MMC_SPARSE_DEVICE_MIN")) ctx->sparse_dev_min = strtoull(e, nullptr, 10);   // test hook: 0 = always sort sparse records on the device
     if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
         long v = atol(e);
@@ -961,7 +981,7 @@ int mmc_batch_acquire(mmc_ctx *ctx, mmc_batch_t **batch) {
     if (rc != MMC_OK) return rc;
     pick->acquired = true; pick->uploaded = false;
     mmc_batch_t &b = pick->pub;
-    b.n_reads = 0; b.cigar_used = b.seq_used = b.mm_used = b.ml_used = 0; b.seq_exc_used = 0;
+    b.n_reads = 0; b.cigar_used = b.seq_used = b.mm_used = b.ml_used = 0; b.seq_exc_used = 0; b.cig8_used = 0;
     *batch = &b;
     return MMC_OK;
 }

@@ -947,6 +947,39 @@ __global__ void __launch_bounds__(256) k_patch_seq4(const unsigned long long *ex
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// CIGAR transport (mmc_batch_t.cig8, include/minimod_cuda.h): ONT alignments have an op per ~17 bases, a third of a
+// whole-genome batch's bytes as 32-bit words.  The packer can send a byte per op (op | min(len,15) << 4) plus two
+// escape lists per read (one byte, then 32 bits, for the lengths that do not fit); this kernel rebuilds BAM's word
+// pool in HBM, word for word, before the decode kernels run.  One warp per read, a lane per op, 32 ops per step; an
+// op's place in the escape lists is its rank among the escaped ops (ballot + popcount, running over the steps).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_cigar(const uint8_t *cig8, const unsigned long long *cig8_off, const uint32_t *n_cigar,
+                                                      const unsigned long long *cigar_off, uint32_t n_reads, uint32_t *cigar) {
+    const uint32_t lane = threadIdx.x & 31u, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_reads; r += n_warps) {
+        const uint8_t *blob = cig8 + cig8_off[r];
+        const uint32_t n = n_cigar[r];
+        const uint32_t n1 = *reinterpret_cast<const uint32_t *>(blob);
+        const uint8_t *ops = blob + 4, *l1 = ops + ((n + 3u) & ~3u);
+        const uint32_t *l2 = reinterpret_cast<const uint32_t *>(l1 + ((n1 + 3u) & ~3u));
+        uint32_t *out = cigar + cigar_off[r];
+        uint32_t c1 = 0, c2 = 0;                                             // escaped ops before this step
+        for (uint32_t base = 0; base < n; base += 32u) {
+            const uint32_t i = base + lane;
+            const uint32_t b = i < n ? ops[i] : 0u;
+            const uint32_t op = b & 15u, l4 = b >> 4;
+            const uint32_t m1 = __ballot_sync(0xffffffffu, l4 == 15u);
+            const uint32_t v = l4 == 15u ? l1[c1 + (uint32_t)__popc(m1 & ((1u << lane) - 1u))] : 0u;
+            const uint32_t m2 = __ballot_sync(0xffffffffu, v == 255u);
+            uint32_t len = l4;
+            if (l4 == 15u) len = v < 255u ? 15u + v : l2[c2 + (uint32_t)__popc(m2 & ((1u << lane) - 1u))];
+            if (i < n) out[i] = (len << 4) | op;
+            c1 += (uint32_t)__popc(m1); c2 += (uint32_t)__popc(m2);
+        }
+    }
+}
+
 struct FinalizeParams {
     const unsigned long long *cells;   // first cell of the scanned range
     unsigned long long n_cells;

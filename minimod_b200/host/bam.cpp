@@ -11,7 +11,7 @@ static inline uint16_t le16(const uint8_t *p) { return (uint16_t)(p[0] | p[1] <<
 // BGZF: gzip member = 12-byte header (XLEN at 10) + extra field with subfield 'B','C',2,BSIZE + raw deflate
 // + CRC32 + ISIZE; BSIZE + 1 is the size of the whole member (SAM spec 4.1).
 // ---------------------------------------------------------------------------------------------------------
-static const size_t kRing = 256;
+static const size_t kRing = 4096;   // blocks in flight: ~256 MB of inflated data can run ahead of the parser (the device start-up and every pause of the consumer are used)
 
 bool BgzfReader::is_bgzf(const std::string &path) {
     FILE *f = fopen(path.c_str(), "rb");

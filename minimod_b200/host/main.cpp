@@ -249,6 +249,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         mo.n_slots = 3; mo.max_reads = (uint64_t)opt.batch_size; mo.max_bytes = (uint64_t)opt.batch_size_bases;
         mo.sparse_capacity = (uint64_t)opt.sparse_cap;
         mo.seq_packing = 2;                          // SEQ crosses PCIe at 2 bits per base + exceptions
+        mo.cigar_packing = 8;                        // CIGARs at a byte per op + escapes
         if (mmc_create(&ctxs[d], &mo, (int32_t)names.size(), names.data(), bam.lens.data()) != MMC_OK) {
             ERROR("%s", mmc_strerror(nullptr)); exit(EXIT_FAILURE);
         }

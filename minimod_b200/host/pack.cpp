@@ -74,6 +74,28 @@ static int64_t pack_seq2(mmc_batch_t *b, uint64_t s0, const uint8_t *seq, uint32
     return (int64_t)(e - e0);
 }
 
+// CIGAR in the byte form of include/minimod_cuda.h (cigar_packing == 8): blob at cig8[at], returns its size, or -1 if it
+// does not fit the pool
+static int64_t pack_cig8(mmc_batch_t *b, uint64_t at, const uint8_t *cig_bytes, uint32_t n) {
+    auto word = [&](uint32_t i) { uint32_t w; memcpy(&w, cig_bytes + 4 * (size_t)i, 4); return w; };   // (BAM records are not aligned)
+    uint32_t n1 = 0, n2 = 0;
+    for (uint32_t i = 0; i < n; ++i) { const uint32_t len = word(i) >> 4; n1 += len >= 15u; n2 += len >= 15u + 255u; }
+    const uint64_t size = 4 + (((uint64_t)n + 3) & ~3ull) + (((uint64_t)n1 + 3) & ~3ull) + 4ull * n2;
+    if (at + size > b->cig8_cap) return -1;
+    uint8_t *p = b->cig8 + at;
+    memcpy(p, &n1, 4);
+    uint8_t *ops = p + 4, *l1 = ops + ((n + 3u) & ~3u), *l2 = l1 + ((n1 + 3u) & ~3u);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t w = word(i), len = w >> 4, op = w & 15u;
+        if (len < 15u) { ops[i] = (uint8_t)(op | (len << 4)); continue; }
+        ops[i] = (uint8_t)(op | 0xf0u);
+        if (len < 15u + 255u) { *l1++ = (uint8_t)(len - 15u); continue; }
+        *l1++ = 255u;
+        memcpy(l2, &len, 4); l2 += 4;
+    }
+    return (int64_t)size;
+}
+
 PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt, BatchMeta *meta) {
     // ---- filters, in the reference's order (src/minimod.c:260-284)
     if (rec.flag & 4) return kSkipped;                                   // BAM_FUNMAP
@@ -96,8 +118,13 @@ PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt
     if (b->n_reads >= b->max_reads || c0 + rec.n_cigar > b->cigar_cap || s0 + seq_bytes > b->seq_cap ||
         m0 + mm_len > b->mm_cap || l0 + ml_len > b->ml_cap)
         return kNoSpace;
-    const bool two_bit = b->seq_packing == 2;
-    int64_t n_exc = 0;
+    const bool two_bit = b->seq_packing == 2, cig_bytes = b->cigar_packing == 8;
+    int64_t n_exc = 0, cig8_size = 0;
+    const uint64_t g0 = up16(b->cig8_used);
+    if (cig_bytes) {                                // written past cig8_used; committed with the other counters below
+        cig8_size = pack_cig8(b, g0, (const uint8_t *)rec.cigar(), rec.n_cigar);
+        if (cig8_size < 0) return kNoSpace;
+    }
     if (two_bit) {                                  // written past seq_used; committed with the other counters below
         n_exc = pack_seq2(b, s0, rec.seq(), (uint32_t)rec.l_qseq);
         if (n_exc < 0) return kNoSpace;
@@ -109,7 +136,8 @@ PackResult pack_record(const BamRecord &rec, mmc_batch_t *b, const LoadOpts &opt
     b->mm_len[i] = (uint32_t)mm_len; b->ml_len[i] = ml_len;
     b->hp[i] = hp_of(rec);
     b->cigar_off[i] = c0; b->seq_off[i] = s0; b->mm_off[i] = m0; b->ml_off[i] = l0;
-    memcpy(b->cigar + c0, rec.cigar(), 4 * (size_t)rec.n_cigar);
+    if (!cig_bytes) memcpy(b->cigar + c0, rec.cigar(), 4 * (size_t)rec.n_cigar);
+    else { b->cig8_off[i] = g0; b->cig8_used = g0 + (uint64_t)cig8_size; }
     if (!two_bit) memcpy(b->seq4 + s0, rec.seq(), seq_bytes);
     else b->seq_exc_used += (uint64_t)n_exc;
     memcpy(b->mm + m0, mm, mm_len);
@@ -144,7 +172,7 @@ int BatchLoader::next_owner(std::string *err) {
 }
 
 int BatchLoader::fill(mmc_batch_t *b, BatchMeta *meta, std::string *err) {
-    b->n_reads = 0; b->cigar_used = b->seq_used = b->mm_used = b->ml_used = 0; b->seq_exc_used = 0;
+    b->n_reads = 0; b->cigar_used = b->seq_used = b->mm_used = b->ml_used = 0; b->seq_exc_used = 0; b->cig8_used = 0;
     meta->stats = BatchStats(); meta->qname_off.clear(); meta->qnames.clear();
     BatchStats &st = meta->stats;
     int batch_owner = -1;

@@ -479,13 +479,35 @@ static uint8_t *seq4_from_transport(const mmc_batch_t *b) {
     return s4;
 }
 
+/* The batch's CIGARs in the byte form (include/minimod_cuda.h, cigar_packing == 8) back to BAM's 32-bit words, one op at
+ * a time with two running cursors into the escape lists.  Only the oracle does this on the CPU. */
+static uint32_t *cigar_from_transport(const mmc_batch_t *b) {
+    uint32_t *w = (uint32_t *)calloc(b->cigar_used + 64, 4);
+    for (uint32_t r = 0; r < b->n_reads; r++) {
+        const uint8_t *blob = b->cig8 + b->cig8_off[r];
+        const uint32_t n = b->n_cigar[r];
+        uint32_t n1; memcpy(&n1, blob, 4);
+        const uint8_t *ops = blob + 4, *l1 = ops + ((n + 3u) & ~3u), *l2 = l1 + ((n1 + 3u) & ~3u);
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t len = ops[i] >> 4;
+            if (len == 15u) {
+                const uint32_t v = *l1++;
+                if (v < 255u) len = 15u + v; else { memcpy(&len, l2, 4); l2 += 4; }
+            }
+            w[b->cigar_off[r] + i] = (len << 4) | (ops[i] & 15u);
+        }
+    }
+    return w;
+}
+
 int oracle_process_batch(oracle_ctx *c, const mmc_batch_t *b_in) {
-    mmc_batch_t tmp;
-    const mmc_batch_t *b = b_in;
+    mmc_batch_t tmp = *b_in;
     uint8_t *s4 = NULL;
-    if (b_in->seq_packing == 2) { tmp = *b_in; s4 = seq4_from_transport(b_in); tmp.seq4 = s4; b = &tmp; }
-    int rc_all = oracle_process_batch4(c, b);
-    free(s4);
+    uint32_t *cw = NULL;
+    if (b_in->seq_packing == 2) { s4 = seq4_from_transport(b_in); tmp.seq4 = s4; }
+    if (b_in->cigar_packing == 8) { cw = cigar_from_transport(b_in); tmp.cigar = cw; }
+    int rc_all = oracle_process_batch4(c, &tmp);
+    free(s4); free(cw);
     return rc_all;
 }
 

@@ -1,5 +1,6 @@
 """Hand-built reads for edge-case tests: write BAM-like fields straight into an mmc_batch_t."""
 import ctypes as C
+import struct
 
 NT16 = "=ACMGRSVTWYHKDBN"
 OPS = "MIDNSHP=XB"
@@ -21,8 +22,19 @@ def add_read(bp, tid, pos, flag, seq, cigar, mm, ml, hp=0):
         else:
             ops.append((int(num) << 4) | OPS.index(ch)); num = ""
     c0, s0, m0, l0 = up16(b.cigar_used * 4) // 4, up16(b.seq_used), up16(b.mm_used), up16(b.ml_used)
-    for k, w in enumerate(ops):
-        b.cigar[c0 + k] = w
+    if b.cigar_packing == 8:        # transport form (include/minimod_cuda.h): a byte per op + two escape lists
+        l1 = [min(255, (w >> 4) - 15) for w in ops if (w >> 4) >= 15]
+        l2 = [w >> 4 for w in ops if (w >> 4) >= 15 + 255]
+        pad = lambda x: x + bytes(-len(x) % 4)
+        blob = struct.pack("<I", len(l1)) + pad(bytes((w & 15) | (min(w >> 4, 15) << 4) for w in ops)) + pad(bytes(l1)) + struct.pack(f"<{len(l2)}I", *l2)
+        g0 = up16(b.cig8_used)
+        assert g0 + len(blob) <= b.cig8_cap
+        C.memmove(C.addressof(b.cig8.contents) + g0, blob, len(blob))
+        b.cig8_off[i] = g0
+        b.cig8_used = g0 + len(blob)
+    else:
+        for k, w in enumerate(ops):
+            b.cigar[c0 + k] = w
     nb = (len(seq) + 1) // 2
     if b.seq_packing == 2:          # transport form (include/minimod_cuda.h): 2 bits per base + exceptions
         code = {1: 0, 2: 1, 4: 2, 8: 3}

@@ -23,7 +23,7 @@ def test_cuda_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(path)
     for sym in declared_symbols():
         assert hasattr(lib, sym), sym
-    assert lib.mmc_abi_version() == 1
+    assert lib.mmc_abi_version() == 2
 
 
 def test_create_fails_loudly_without_a_device(host_lib):

@@ -128,7 +128,7 @@ for t in sorted(mine):                                     # reads are sorted by
     if not idx: continue
     assert idx == list(range(idx[0], idx[-1] + 1))
     b = pair.batch.contents                                # the packer appends: start every batch empty
-    b.n_reads = 0; b.cigar_used = 0; b.seq_used = 0; b.mm_used = 0; b.ml_used = 0; b.seq_exc_used = 0
+    b.n_reads = 0; b.cigar_used = 0; b.seq_used = 0; b.mm_used = 0; b.ml_used = 0; b.seq_exc_used = 0; b.cig8_used = 0
     got, _ = s.fill(pair.batch, idx[0], len(idx), 2); assert got == len(idx)
     rc, msg = pair.run_device(); assert rc == 0, msg
     n_mine += len(idx)

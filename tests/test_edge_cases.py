@@ -26,6 +26,17 @@ def test_edge_cases_emulated_two_bit_seq(emul_lib, monkeypatch):
         run_fatal(emul_lib, case)
 
 
+def test_edge_cases_emulated_byte_cigar(emul_lib, monkeypatch):
+    """Every edge case again with the CIGARs in their byte form (lengths 0..14 in the nibble, 15..269 in the first escape
+    list, the huge ops of `huge_cigar_ops` in the second); the oracle decodes the form with its own sequential loop."""
+    monkeypatch.setenv("MMC_CIGAR_PACKING", "8")
+    monkeypatch.setenv("MMC_SEQ_PACKING", "2")
+    for case in CASES:
+        run_case(emul_lib, case)
+    for case in FATAL:
+        run_fatal(emul_lib, case)
+
+
 def test_view_buffer_regrows(emul_lib):
     """A view batch with more rows than the slot's record buffer: the buffer is regrown and the batch re-run
     (it used to fail with 'raise view_capacity', an option the CLI does not have)."""

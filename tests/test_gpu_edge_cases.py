@@ -23,3 +23,13 @@ def test_edge_cases_cuda_two_bit_seq(cuda_lib, monkeypatch):
         run_case(cuda_lib, case)
     for case in FATAL:
         run_fatal(cuda_lib, case)
+
+
+def test_edge_cases_cuda_byte_cigar(cuda_lib, monkeypatch):
+    """Every edge case again with the CIGARs in their byte form (k_unpack_cigar rebuilds the word pool on the device)."""
+    monkeypatch.setenv("MMC_CIGAR_PACKING", "8")
+    monkeypatch.setenv("MMC_SEQ_PACKING", "2")
+    for case in CASES:
+        run_case(cuda_lib, case)
+    for case in FATAL:
+        run_fatal(cuda_lib, case)
