@@ -93,7 +93,7 @@ typedef struct {
     uint64_t max_bytes;          /* per-batch capacity in payload bytes (-B): cigar+seq+mm+ml pools */
     uint64_t sparse_capacity;    /* records in the side buffer for cells outside the dense arrays
                                     (ins_offset>0, HP>=dense_haps, code id>=dense_codes); 0 -> default */
-    int32_t  dense_haps;         /* haplotype values 0..dense_haps-1 get dense strata; 0 -> 4 */
+    int32_t  dense_haps;         /* haplotype values 0..dense_haps-1 get dense strata; 0 -> 3 ('*' + HP 0,1,2: one 32-byte sector) */
     int32_t  dense_codes;        /* with a wildcard code: dense code slots; 0 -> 8 */
     uint64_t view_capacity;      /* VIEW: records per batch; 0 -> derived from max_bytes */
     /* optional explicit pool capacities per batch (0 -> derived from max_bytes) */

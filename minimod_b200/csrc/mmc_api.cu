@@ -660,7 +660,10 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     if (o.n_slots <= 0) o.n_slots = 3;
     if (o.max_reads == 0) o.max_reads = 512;                 // init_opt(), src/minimod.c:487
     if (o.max_bytes == 0) o.max_bytes = 20 * 1000 * 1000;    // src/minimod.c:488
-    if (o.dense_haps <= 0) o.dense_haps = 4;
+    // '*' + HP 0..2 = four 8-byte strata = exactly one 32-byte sector per (position, strand, code): the two reductions of a
+    // call (src/mod.c:906-928) land in ONE sector and a position's hot cells take one L2 sector instead of 1.75 on average
+    // (config 4: 84 % of the reductions' sectors missed L2 with five strata, profiles/r02_n1_l2_atomics.txt)
+    if (o.dense_haps <= 0) o.dense_haps = 3;
     if (o.dense_codes <= 0) o.dense_codes = 8;
     if (o.dense_haps > 255) o.dense_haps = 255;
     ctx->mods.assign(opts->mods, opts->mods + opts->n_mods);
