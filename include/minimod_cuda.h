@@ -25,8 +25,10 @@
  * (src/error.h:94-152).  There is no CPU fallback: if no CUDA device is usable,
  * mmc_create() fails.
  *
- * Threading: one host thread may fill/submit batches while another waits on
- * them; calls on one context are otherwise not re-entrant.
+ * Threading: a context is used from one host thread at a time (its error string,
+ * timers and slot states are not synchronised); the pinned arrays of an acquired
+ * batch may be FILLED by any thread, which is where the host's time goes.  Several
+ * contexts (one per device) may be driven from different threads.
  */
 #ifndef MINIMOD_CUDA_H
 #define MINIMOD_CUDA_H

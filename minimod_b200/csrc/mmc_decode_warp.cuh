@@ -789,10 +789,13 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
     // as flags and raised after the loop.  Exact while every length is < 2^24 (128 x 2^24 = 2^31).
     uint32_t bad = 0;                                                                // 1 hard clip, 2 unhandled op, 4 CIGAR past the read, 8 past the contig
     const uint32_t insq = P.insertions ? 0x183u : 0x181u;                            // ops whose query range must lie inside the read: M = X (+ I)
+    uint4 w4_next = make_uint4(0, 0, 0, 0);
+    if (lane * 4u < n_cig) w4_next = ld16(reinterpret_cast<const uint8_t *>(cig + lane * 4u));   // (the pool has 64 bytes of slack past the last slice)
     for (uint32_t base = 0; base < n_cig; base += 128u) {
         const uint32_t i0 = base + lane * 4u;
-        uint4 w4 = make_uint4(0, 0, 0, 0);
-        if (i0 < n_cig) w4 = ld16(reinterpret_cast<const uint8_t *>(cig + i0));     // (the pool has 64 bytes of slack past the last slice)
+        const uint4 w4 = w4_next;                                                    // the next step's words are on their way while this step scans and stores
+        w4_next = make_uint4(0, 0, 0, 0);
+        if (i0 + 128u < n_cig) w4_next = ld16(reinterpret_cast<const uint8_t *>(cig + i0 + 128u));
         const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
         uint32_t qlv[4], rlv[4], sq = 0, sr = 0;
 #pragma unroll
