@@ -15,6 +15,8 @@
 #include <chrono>
 #ifndef MMC_EMUL
 #include <dlfcn.h>
+#include <strings.h>
+#include <unistd.h>
 #endif
 #include <vector>
 
@@ -37,7 +39,7 @@ static_assert(sizeof(FreqRecDev) == 24, "record size");
 namespace {
 
 constexpr size_t kSlack = 64;                 // readable bytes after the last slice of a pool
-constexpr uint32_t kTileCells = 8192;         // cells per finalize tile
+constexpr uint32_t kTileCells = 32768;        // cells per finalize tile (256 KB: one CTA; the tile scan is a single CTA, so tiles are large)
 constexpr uint32_t kExcCap = 1u << 22;        // exception-run starts per contig
 
 std::string g_create_error;
@@ -125,6 +127,7 @@ struct mmc_ctx {
     uint32_t *d_tile_count = nullptr; unsigned long long *d_tile_off = nullptr, *d_totals = nullptr;
     size_t fin_tiles_cap = 0, fin_jobs_cap = 0;
     uint32_t *d_fin_mask = nullptr;                                  // one bit per scanned cell (+ 1 word: n_called overflow flag)
+    FinJob *d_fin_jobs = nullptr;                                    // the contig ranges of one finalize / drain (fin_jobs_cap entries)
     FreqRecDev *d_rows = nullptr; size_t d_rows_cap = 0;
     // device-side finalize of the sparse side buffer (mmc_sparse.cuh): grow-only scratch
     uint64_t sparse_dev_min = 1u << 16;                              // fewer records than this: host sort (a few ms at most)
@@ -140,7 +143,7 @@ struct mmc_ctx {
     cudaEvent_t ev_reset = nullptr; bool reset_pending = false;    // mmc_freq_reset() clears on fin_stream; the next decode launches wait for it on the device
     std::vector<int32_t> reset_touch;                              // (source of its asynchronous copy)
     mmc_freq_rec_t *h_drain[2] = {nullptr, nullptr}; size_t h_drain_cap[2] = {0, 0}; int drain_flip = 0;   // pinned, alternating
-    unsigned long long *h_totals = nullptr;                        // pinned, fin_jobs_cap entries
+    unsigned long long *h_totals = nullptr;                        // pinned: [0] rows of the pass, [1] overflow flag
     cudaEvent_t ev_d0 = nullptr, ev_d1 = nullptr;
     // results
     std::vector<uint32_t> need_tmp;
@@ -877,6 +880,7 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (ctx->ev_d0) cudaEventDestroy(ctx->ev_d0);
     if (ctx->ev_d1) cudaEventDestroy(ctx->ev_d1);
     if (ctx->ev_reset) cudaEventDestroy(ctx->ev_reset);
+    if (ctx->d_fin_jobs) cudaFree(ctx->d_fin_jobs);
     if (ctx->ev_f0) cudaEventDestroy(ctx->ev_f0);
     if (ctx->ev_f1) cudaEventDestroy(ctx->ev_f1);
     if (ctx->fin_stream) cudaStreamDestroy(ctx->fin_stream);
@@ -1251,39 +1255,42 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
             ctx->fin_tiles_cap = tiles;
         }
         if (jobs.size() > ctx->fin_jobs_cap) {
-            if (ctx->d_totals) cudaFree(ctx->d_totals);
-            if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
-            ctx->d_totals = nullptr; ctx->h_totals = nullptr; ctx->fin_jobs_cap = 0;
-            CU(ctx, cudaMalloc((void **)&ctx->d_totals, 8 * jobs.size()));
-            CU(ctx, cudaMallocHost((void **)&ctx->h_totals, 8 * jobs.size()));
+            if (ctx->d_fin_jobs) cudaFree(ctx->d_fin_jobs);
+            ctx->d_fin_jobs = nullptr; ctx->fin_jobs_cap = 0;
+            CU(ctx, cudaMalloc((void **)&ctx->d_fin_jobs, sizeof(FinJob) * jobs.size()));
             ctx->fin_jobs_cap = jobs.size();
         }
-        uint32_t *d_overflow = ctx->d_fin_mask + ctx->fin_tiles_cap * (kTileCells / 32);
-        CU(ctx, cudaMemsetAsync(d_overflow, 0, 4, ctx->fin_stream));
-        std::vector<FinalizeParams> fps(jobs.size());
+        if (!ctx->d_totals) {
+            CU(ctx, cudaMalloc((void **)&ctx->d_totals, 8));
+            CU(ctx, cudaMallocHost((void **)&ctx->h_totals, 16));
+        }
+        // ONE launch per pass over every contig range (a whole-genome finalize used to be 3 launches x 195 contigs)
+        std::vector<FinJob> fj(jobs.size());
         for (size_t k = 0; k < jobs.size(); ++k) {
             const Job &j = jobs[k];
-            FinalizeParams &fp = fps[k];
-            memset(&fp, 0, sizeof(fp));
-            fp.cells = ctx->contigs[j.tid].dev.cells + (uint64_t)j.lo * spp;
-            fp.n_cells = j.n_cells; fp.tid = j.tid; fp.lo = j.lo;
-            fp.n_code_slots = ctx->n_code_slots; fp.n_hap_slots = ctx->n_hap_slots; fp.haplotypes = ctx->opts.haplotypes;
-            fp.tile_count = ctx->d_tile_count + j.tile0; fp.tile_offset = ctx->d_tile_off + j.tile0; fp.cells_per_tile = kTileCells;
-            fp.mask = ctx->d_fin_mask + j.tile0 * (kTileCells / 32); fp.overflow = d_overflow;
-            MMC_LAUNCH(k_count_nonzero, (unsigned)j.n_tiles, 256u, ctx->fin_stream, fp);
-            CU(ctx, cudaGetLastError());
-            MMC_LAUNCH(k_scan_tiles, 1u, 256u, ctx->fin_stream, fp.tile_count, fp.tile_offset, (uint32_t)j.n_tiles, ctx->d_totals + k);
-            CU(ctx, cudaGetLastError());
-            ctx->tm.kernel_launches += 2;
+            fj[k].cells = ctx->contigs[j.tid].dev.cells + (uint64_t)j.lo * spp;
+            fj[k].n_cells = j.n_cells; fj[k].tile0 = j.tile0; fj[k].tid = j.tid; fj[k].lo = j.lo;
         }
-        CU(ctx, cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 8 * jobs.size(), cudaMemcpyDeviceToHost, ctx->fin_stream));
-        uint32_t h_overflow = 0;
-        CU(ctx, cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->fin_stream));
-        CU(ctx, cudaStreamSynchronize(ctx->fin_stream));
-        if (h_overflow)                                       // src/mod.c:899-901,922-924: the reference aborts too
+        CU(ctx, cudaMemcpyAsync(ctx->d_fin_jobs, fj.data(), sizeof(FinJob) * fj.size(), cudaMemcpyHostToDevice, ctx->fin_stream));
+        uint32_t *d_overflow = ctx->d_fin_mask + ctx->fin_tiles_cap * (kTileCells / 32);
+        CU(ctx, cudaMemsetAsync(d_overflow, 0, 4, ctx->fin_stream));
+        FinalizeParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.jobs = ctx->d_fin_jobs; fp.n_jobs = (uint32_t)jobs.size();
+        fp.n_code_slots = ctx->n_code_slots; fp.n_hap_slots = ctx->n_hap_slots; fp.haplotypes = ctx->opts.haplotypes;
+        fp.tile_count = ctx->d_tile_count; fp.tile_offset = ctx->d_tile_off; fp.cells_per_tile = kTileCells;
+        fp.mask = ctx->d_fin_mask; fp.overflow = d_overflow;
+        MMC_LAUNCH(k_count_nonzero, (unsigned)tiles, 256u, ctx->fin_stream, fp);
+        CU(ctx, cudaGetLastError());
+        MMC_LAUNCH(k_scan_tiles, 1u, 256u, ctx->fin_stream, fp.tile_count, fp.tile_offset, (uint32_t)tiles, ctx->d_totals);
+        CU(ctx, cudaGetLastError());
+        ctx->tm.kernel_launches += 2;
+        CU(ctx, cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 8, cudaMemcpyDeviceToHost, ctx->fin_stream));
+        CU(ctx, cudaMemcpyAsync(ctx->h_totals + 1, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->fin_stream));
+        CU(ctx, cudaStreamSynchronize(ctx->fin_stream));     // (also: fj has been copied)
+        if ((uint32_t)ctx->h_totals[1])                      // src/mod.c:899-901,922-924: the reference aborts too
             return fail(ctx, MMC_ENOMEM, "n_called overflowed for a position (more than 4294967295 calls on one cell). Please report this issue.");
-        uint64_t total = 0;
-        for (size_t k = 0; k < jobs.size(); ++k) total += ctx->h_totals[k];
+        const uint64_t total = ctx->h_totals[0];
         if (total) {
             if (total > ctx->d_rows_cap) {
                 if (ctx->d_rows) cudaFree(ctx->d_rows);
@@ -1292,15 +1299,10 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
                 CU(ctx, cudaMalloc((void **)&ctx->d_rows, sizeof(FreqRecDev) * cap));
                 ctx->d_rows_cap = cap;
             }
-            uint64_t base = 0;
-            for (size_t k = 0; k < jobs.size(); ++k) {
-                if (!ctx->h_totals[k]) continue;
-                fps[k].out = ctx->d_rows; fps[k].out_base = base;
-                MMC_LAUNCH(k_emit_records, (unsigned)jobs[k].n_tiles, 256u, ctx->fin_stream, fps[k]);
-                CU(ctx, cudaGetLastError());
-                ctx->tm.kernel_launches += 1;
-                base += ctx->h_totals[k];
-            }
+            fp.out = ctx->d_rows;
+            MMC_LAUNCH(k_emit_records, (unsigned)tiles, 256u, ctx->fin_stream, fp);
+            CU(ctx, cudaGetLastError());
+            ctx->tm.kernel_launches += 1;
             n_dense = total;
         }
     }
@@ -1599,7 +1601,11 @@ int mmc_region_reduce(mmc_ctx *const *ctxs, int32_t n_ctx, int32_t tid, double *
     init_all_t p_init = nullptr; allreduce_t p_ar = nullptr; void_t p_gs = nullptr, p_ge = nullptr; destroy_t p_destroy = nullptr; errstr_t p_err = nullptr;
     std::vector<comm_t> comms(n_ctx, nullptr);
     if (!same_device) {
-        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);         // stdout is the tool's data channel: NCCL's version / debug lines go to stderr
+        // stdout is the tool's data channel.  NCCL's debug lines follow NCCL_DEBUG_FILE -- except at NCCL_DEBUG=VERSION (what
+        // this image exports), where the "NCCL version ..." line is printed to stdout regardless: that level is raised to WARN
+        // (same line, now through the debug file), and stdout itself points at stderr while the communicators are created.
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+        { const char *lv = getenv("NCCL_DEBUG"); if (lv && !strcasecmp(lv, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1); }
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (!h) return fail(c0, MMC_ECUDA, "mmc_region_reduce: contexts on several devices need NCCL, but libnccl.so.2 cannot be loaded (%s)", dlerror());
         p_init = (init_all_t)dlsym(h, "ncclCommInitAll"); p_ar = (allreduce_t)dlsym(h, "ncclAllReduce");
@@ -1608,7 +1614,11 @@ int mmc_region_reduce(mmc_ctx *const *ctxs, int32_t n_ctx, int32_t tid, double *
         if (!p_init || !p_ar || !p_gs || !p_ge || !p_destroy) return fail(c0, MMC_ECUDA, "mmc_region_reduce: libnccl.so.2 lacks the expected symbols");
         std::vector<int> devs(n_ctx);
         for (int k = 0; k < n_ctx; ++k) devs[k] = ctxs[k]->opts.device;
+        fflush(stdout);
+        const int saved_out = dup(1);
+        if (saved_out >= 0) dup2(2, 1);
         const int rc = p_init(comms.data(), n_ctx, devs.data());
+        if (saved_out >= 0) { fflush(stdout); dup2(saved_out, 1); close(saved_out); }
         if (rc != 0) return fail(c0, MMC_ECUDA, "ncclCommInitAll failed: %s", p_err ? p_err(rc) : "?");
     }
 #endif

@@ -980,46 +980,64 @@ __global__ void __launch_bounds__(256) k_unpack_cigar(const uint8_t *cig8, const
     }
 }
 
-struct FinalizeParams {
+// One launch covers every contig range of a finalize / drain: a job per range, tiles numbered across the jobs.
+struct FinJob {
     const unsigned long long *cells;   // first cell of the scanned range
     unsigned long long n_cells;
+    unsigned long long tile0;          // number of this job's first tile
     int32_t tid;
     int32_t lo;                        // contig position of cells[0]
+};
+struct FinalizeParams {
+    const FinJob *jobs;                // sorted by tile0
+    uint32_t n_jobs;
     int32_t n_code_slots, n_hap_slots, haplotypes;
     uint32_t *tile_count;              // per tile (CTA-sized range of cells)
-    unsigned long long *tile_offset;   // exclusive scan of tile_count (+ running base)
+    unsigned long long *tile_offset;   // exclusive scan of tile_count over all tiles of all jobs
     uint32_t cells_per_tile;
     void *out;                         // mmc_freq_rec_t[]
-    unsigned long long out_base;
-    uint32_t *mask;                    // one bit per cell of the range: non-zero (written by k_count_nonzero, read by k_emit_records)
+    uint32_t *mask;                    // one bit per cell of every tile: non-zero (written by k_count_nonzero, read by k_emit_records)
     uint32_t *overflow;                // set when a cell shows n_mod > n_called: n_called wrapped (src/mod.c:899-901)
 };
+__device__ __forceinline__ FinJob fin_job_of(const FinalizeParams &p, unsigned long long tile) {
+    uint32_t lo = 0, hi = p.n_jobs - 1u;                          // last job with tile0 <= tile
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1u) >> 1; if (p.jobs[mid].tile0 <= tile) lo = mid; else hi = mid - 1u; }
+    return p.jobs[lo];
+}
 
 // Pass 1 of the compaction: the only full read of the dense range.  One CTA (8 warps) per tile; every warp owns a contiguous
 // eighth of the tile and leaves one ballot word per 32 cells, so that pass 2 never touches an empty cell again.
-__global__ void __launch_bounds__(256) k_count_nonzero(FinalizeParams p) {
+__global__ void __launch_bounds__(256) k_count_nonzero(const __grid_constant__ FinalizeParams p) {
     __shared__ uint32_t ws[8];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned long long c0 = (unsigned long long)blockIdx.x * p.cells_per_tile;
+    const FinJob j = fin_job_of(p, blockIdx.x);
+    const unsigned long long c0 = ((unsigned long long)blockIdx.x - j.tile0) * p.cells_per_tile;
     unsigned long long c1 = c0 + p.cells_per_tile;
-    if (c1 > p.n_cells) c1 = p.n_cells;
+    if (c1 > j.n_cells) c1 = j.n_cells;
     const uint32_t per_warp = p.cells_per_tile / 8u;
     unsigned long long w0 = c0 + (unsigned long long)warp * per_warp, w1 = w0 + per_warp;
     if (w0 > c1) w0 = c1;
     if (w1 > c1) w1 = c1;
+    uint32_t *mask = p.mask + (unsigned long long)blockIdx.x * (p.cells_per_tile / 32u) + warp * (per_warp / 32u);
     uint32_t cnt = 0, myword = 0, bad = 0;
     const uint32_t n_words = (uint32_t)((w1 - w0 + 31u) >> 5);
-    for (uint32_t w = 0; w < n_words; w += 2u) {                  // two loads in flight per lane
-        const unsigned long long ca = w0 + (unsigned long long)w * 32u + lane, cb = ca + 32u;
-        const unsigned long long va = ca < w1 ? p.cells[ca] : 0ull, vb = cb < w1 ? p.cells[cb] : 0ull;
-        const uint32_t fa = __ballot_sync(0xffffffffu, va != 0ull), fb = __ballot_sync(0xffffffffu, vb != 0ull);
-        bad |= (uint32_t)((uint32_t)(va >> 32) > (uint32_t)va) | (uint32_t)((uint32_t)(vb >> 32) > (uint32_t)vb);
-        if (lane == (w & 31u)) myword = fa;
-        if (lane == ((w + 1u) & 31u)) myword = fb;
-        cnt += (uint32_t)__popc(fa) + (uint32_t)__popc(fb);
-        if (((w + 2u) & 31u) == 0u || w + 2u >= n_words) {          // 32 words collected (or the slice ends): one coalesced store
+    for (uint32_t w = 0; w < n_words; w += 4u) {                  // four loads in flight per lane
+        unsigned long long v[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const unsigned long long c = w0 + (unsigned long long)(w + k) * 32u + lane;
+            v[k] = c < w1 ? j.cells[c] : 0ull;
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t f = __ballot_sync(0xffffffffu, v[k] != 0ull);
+            bad |= (uint32_t)((uint32_t)(v[k] >> 32) > (uint32_t)v[k]);
+            if (lane == ((w + k) & 31u)) myword = f;
+            cnt += (uint32_t)__popc(f);
+        }
+        if (((w + 4u) & 31u) == 0u || w + 4u >= n_words) {          // 32 words collected (or the slice ends): one coalesced store
             const uint32_t first = w & ~31u, mine = first + lane;
-            if (mine < n_words) p.mask[(w0 >> 5) + mine] = myword;
+            if (mine < n_words) mask[mine] = myword;
             myword = 0;
         }
     }
@@ -1063,21 +1081,23 @@ struct FreqRecDev {                    // == mmc_freq_rec_t
 // Pass 2: one CTA (8 warps) per non-empty tile, one barrier per tile.  Every warp owns a contiguous eighth of the tile; it
 // reads the ballot words pass 1 left (32 words = 1024 cells per load), the warp totals are prefix-summed through shared
 // memory, and only the non-zero cells are fetched again and written as rows in cell order.
-__global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
+__global__ void __launch_bounds__(256) k_emit_records(const __grid_constant__ FinalizeParams p) {
     __shared__ uint32_t ws[8];
     if (p.tile_count[blockIdx.x] == 0u) return;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
-    const unsigned long long c0 = (unsigned long long)blockIdx.x * p.cells_per_tile;
+    const FinJob j = fin_job_of(p, blockIdx.x);
+    const unsigned long long c0 = ((unsigned long long)blockIdx.x - j.tile0) * p.cells_per_tile;
     unsigned long long c1 = c0 + p.cells_per_tile;
-    if (c1 > p.n_cells) c1 = p.n_cells;
+    if (c1 > j.n_cells) c1 = j.n_cells;
     const uint32_t per_warp = p.cells_per_tile / 8u;
     unsigned long long w0 = c0 + (unsigned long long)warp * per_warp, w1 = w0 + per_warp;
     if (w0 > c1) w0 = c1;
     if (w1 > c1) w1 = c1;
+    const uint32_t *mask = p.mask + (unsigned long long)blockIdx.x * (p.cells_per_tile / 32u) + warp * (per_warp / 32u);
     const uint32_t n_words = (uint32_t)((w1 - w0 + 31u) >> 5);
     uint32_t cnt = 0;
     for (uint32_t wb = 0; wb < n_words; wb += 32u) {
-        const uint32_t m = wb + lane < n_words ? p.mask[(w0 >> 5) + wb + lane] : 0u;
+        const uint32_t m = wb + lane < n_words ? mask[wb + lane] : 0u;
         uint32_t c = (uint32_t)__popc(m);
 #pragma unroll
         for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
@@ -1088,10 +1108,10 @@ __global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
     if (cnt == 0u) return;
     uint32_t running = 0;
     for (uint32_t w = 0; w < warp; ++w) running += ws[w];
-    FreqRecDev *out = reinterpret_cast<FreqRecDev *>(p.out) + p.out_base + p.tile_offset[blockIdx.x];
+    FreqRecDev *out = reinterpret_cast<FreqRecDev *>(p.out) + p.tile_offset[blockIdx.x];
     const uint32_t spp = 2u * (uint32_t)p.n_code_slots * (uint32_t)p.n_hap_slots;   // slots per position
     for (uint32_t wb = 0; wb < n_words; wb += 32u) {
-        const uint32_t mword = wb + lane < n_words ? p.mask[(w0 >> 5) + wb + lane] : 0u;
+        const uint32_t mword = wb + lane < n_words ? mask[wb + lane] : 0u;
         uint32_t todo = __ballot_sync(0xffffffffu, mword != 0u);                  // words of this group with any non-zero cell
         while (todo) {
             const uint32_t wi = (uint32_t)__ffs((int)todo) - 1u;
@@ -1099,14 +1119,14 @@ __global__ void __launch_bounds__(256) k_emit_records(FinalizeParams p) {
             const uint32_t f = __shfl_sync(0xffffffffu, mword, (int)wi);
             if ((f >> lane) & 1u) {
                 const unsigned long long cc = w0 + (unsigned long long)(wb + wi) * 32u + lane;
-                const unsigned long long v = p.cells[cc];
+                const unsigned long long v = j.cells[cc];
                 const uint32_t at = running + (uint32_t)__popc(f & lt);
                 const unsigned long long posi = cc / spp;
                 uint32_t slot = (uint32_t)(cc - posi * spp);
                 const uint32_t hslot = slot % (uint32_t)p.n_hap_slots; slot /= (uint32_t)p.n_hap_slots;
                 const uint32_t code = slot % (uint32_t)p.n_code_slots; slot /= (uint32_t)p.n_code_slots;
                 FreqRecDev rec;
-                rec.tid = p.tid; rec.pos = p.lo + (int32_t)posi;
+                rec.tid = j.tid; rec.pos = j.lo + (int32_t)posi;
                 rec.n_called = (uint32_t)v; rec.n_mod = (uint32_t)(v >> 32);
                 rec.ins_offset = 0;
                 rec.hap = p.haplotypes ? (int16_t)((int32_t)hslot - 1) : (int16_t)-1;
