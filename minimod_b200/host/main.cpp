@@ -109,6 +109,8 @@ static void print_help(FILE *fp, const Opt &o, const char *tool) {
 
 static int run_tool(int subtool, int argc, char *argv[]) {
     const double realtime0 = realtime();
+    const bool trace = getenv("MINIMOD_TRACE") != nullptr;       // wall-clock stamps of the tool's phases (stderr)
+    auto stamp = [&](const char *what) { if (trace) fprintf(stderr, "[trace] %8.3f s  %s\n", realtime() - realtime0, what); };
     const char *tool = subtool == MMC_FREQ ? "freq" : "view";
     const char *func = subtool == MMC_FREQ ? "freq_main" : "view_main";
     static struct option long_options[] = {
@@ -255,6 +257,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         }
     }
     mmc_ctx *ctx = ctxs[0];
+    stamp("BAM header read, device contexts created");
 
     // ---- reference: FASTA parsing on the host, packing + context evaluation on the device that owns the contig
     double realtime1 = realtime();
@@ -285,6 +288,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         fprintf(stderr, "[%s] Reference contexts loaded in %.3f sec\n", func, realtime() - realtime2);
     }
 
+    stamp("reference packed on the device");
     OutOpts oo; oo.bedmethyl = opt.bedmethyl; oo.insertions = opt.insertions; oo.haplotypes = opt.haplotypes;
     if (subtool == MMC_FREQ) print_freq_header(opt.out, oo); else print_view_header(opt.out, oo);
 
@@ -438,6 +442,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         for (int i = 0; i < n_slots; ++i)
             if (rings[d].b[i] && mmc_batch_release(ctxs[d], rings[d].b[i]) != MMC_OK) die_read(ctxs[d], rings[d].meta[i]);
 
+    stamp("last batch submitted and released");
     double sort_time = 0, halo_ms = 0;
     uint64_t halo_bytes = 0;
     if (stream_rows) {
@@ -527,6 +532,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         output_time += realtime() - o0;
     }
     if (opt.out != stdout) fclose(opt.out); else fflush(stdout);
+    stamp("table finalized, formatted and written");
 
     mmc_timers_t tm;
     memset(&tm, 0, sizeof(tm));
@@ -557,6 +563,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
                           big_tid >= 0 ? "longest contig cut by read start, the others dealt by length" : "contigs dealt by length", halo_ms, halo_bytes / 1e6);
     fprintf(stderr, "\n");
     for (mmc_ctx *c : ctxs) mmc_destroy(c);
+    stamp("device contexts destroyed");
     return 0;
 }
 
