@@ -84,9 +84,8 @@ __device__ __forceinline__ RowKey row_key(const FreqRecDev &r) {
 }
 __device__ __forceinline__ bool key_less(const RowKey &x, const RowKey &y) { return x.hi != y.hi ? x.hi < y.hi : x.lo < y.lo; }
 
-// number of rows of v[0..n) whose key is < k  (no key occurs in both lists)
-__device__ __forceinline__ unsigned long long rows_below(const FreqRecDev *v, unsigned long long n, const RowKey &k) {
-    unsigned long long lo = 0, hi = n;
+// number of rows of v[lo..hi) (+ lo) whose key is < k  (no key occurs in both lists)
+__device__ __forceinline__ unsigned long long rows_below(const FreqRecDev *v, unsigned long long lo, unsigned long long hi, const RowKey &k) {
     while (lo < hi) {
         const unsigned long long mid = (lo + hi) >> 1;
         if (key_less(row_key(v[mid]), k)) lo = mid + 1; else hi = mid;
@@ -94,18 +93,31 @@ __device__ __forceinline__ unsigned long long rows_below(const FreqRecDev *v, un
     return lo;
 }
 
+// Both lists are ordered, so the rows a CTA takes in one step (blockDim.x consecutive rows of one list) fall between the places
+// of the step's first and last row in the other list: two full-length searches per step, every other thread searches that
+// window only (a few steps instead of log2 of millions).
 __global__ void __launch_bounds__(kSpThreads) k_merge_rows(const FreqRecDev *dense, unsigned long long n_dense, const FreqRecDev *sparse, unsigned long long n_sparse,
                                                            FreqRecDev *out) {
-    const unsigned long long total = n_dense + n_sparse;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
-        if (i < n_dense) {
-            const FreqRecDev r = dense[i];
-            out[i + rows_below(sparse, n_sparse, row_key(r))] = r;
-        } else {
-            const unsigned long long j = i - n_dense;
-            const FreqRecDev r = sparse[j];
-            out[j + rows_below(dense, n_dense, row_key(r))] = r;
+    __shared__ unsigned long long win[2];
+    const unsigned long long total = n_dense + n_sparse, step = blockDim.x;
+    const unsigned long long steps_d = (n_dense + step - 1) / step, steps = steps_d + (n_sparse + step - 1) / step;
+    (void)total;
+    for (unsigned long long st = blockIdx.x; st < steps; st += gridDim.x) {
+        const bool from_dense = st < steps_d;
+        const FreqRecDev *mine = from_dense ? dense : sparse, *other = from_dense ? sparse : dense;
+        const unsigned long long n_mine = from_dense ? n_dense : n_sparse, n_other = from_dense ? n_sparse : n_dense;
+        const unsigned long long i0 = (from_dense ? st : st - steps_d) * step, i1 = i0 + step < n_mine ? i0 + step : n_mine;
+        if (threadIdx.x < 2u) {
+            const FreqRecDev r = mine[threadIdx.x == 0u ? i0 : i1 - 1u];
+            win[threadIdx.x] = rows_below(other, 0, n_other, row_key(r));
         }
+        __syncthreads();
+        const unsigned long long i = i0 + threadIdx.x;
+        if (i < i1) {
+            const FreqRecDev r = mine[i];
+            out[i + rows_below(other, win[0], win[1], row_key(r))] = r;
+        }
+        __syncthreads();
     }
 }
 

@@ -25,6 +25,6 @@ for i in 1 2; do
 done
 echo -n "minimod_ref   freq: "; wall oracle/_ref/minimod_ref freq $ARGS -t $T -K 4092 -B 100M -o $D/ref.bed $D/ref.fa $D/reads.bam 2> $D/ref.err
 grep -E "Data loading time|Data processing time|Data merging time|Data output time|Sorting" $D/ref.err | sed 's/^/  ref: /'
-grep -E "time|GPU" $D/mine.err | tail -8 | sed 's/^/  mine: /'
+grep -E "time|GPU|trace|mmc_create|Rows" $D/mine.err | tail -24 | sed 's/^/  mine: /'
 if cmp -s $D/mine.bed $D/ref.bed; then echo "outputs byte-identical ($(wc -l < $D/mine.bed) rows)"; else LC_ALL=C sort $D/mine.bed > $D/a; LC_ALL=C sort $D/ref.bed > $D/b; cmp $D/a $D/b && echo "outputs identical after LC_ALL=C sort ($(wc -l < $D/mine.bed) rows; rows sharing (contig,pos) have no defined order in the reference)"; fi
 rm -rf $D
