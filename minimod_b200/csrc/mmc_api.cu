@@ -73,6 +73,7 @@ struct Slot {
     uint32_t max_cig = 0, max_l = 0; uint64_t pool_need = 0; int variant = 3;   // analyse_batch()
     uint32_t min_tid = 0xffffffffu, min_pos = 0;   // first read of the batch in coordinate order (analyse_batch; unmapped sorts last)
     bool use_stream = false;                   // this batch goes through k_decode_stream (long CIGARs / long reads) instead of k_decode_warp<PRE>
+    uint32_t s_split = 0;                      // k_decode_stream: (read, even / odd blocks) work units (analyse_batch)
     int s_ctas = 8; uint32_t s_arena = 0, s_setup_flex = 4608;   // k_decode_stream: CTAs per SM, arena bytes per warp; k_flat_setup's room for dir | cq | cr
 };
 
@@ -99,6 +100,7 @@ struct mmc_ctx {
     int stream_path = 1;                       // k_flat_setup + k_decode_stream (default): streaming merge, constant shared memory per warp
     uint32_t s_head = 256;                     // k_decode_stream: bytes of call LUTs in front of the arenas
     int s_minb = 6;                            // k_decode_stream<MINB>: resident CTAs per SM the registers are bounded for (MMC_STREAM_MINB)
+    int s_split_mode = -1;                     // -1: per batch (long reads with several MM blocks and haplotype strata); 0 / 1: MMC_STREAM_SPLIT
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
@@ -340,6 +342,22 @@ void analyse_batch(mmc_ctx *ctx, Slot &s) {
         }
         (void)p95;
         s.s_ctas = ctx->s_minb;
+        // split the blocks of a read over two warps?  Only where the window of count cells the reads in flight cover outgrows
+        // the L2: long reads with several strata per cell -- and only if the reads have more than one block (a look at the
+        // MM text of three reads; a wrong guess costs a no-op work unit per read, never a result).
+        s.s_split = 0;
+        if (ctx->s_split_mode >= 0) s.s_split = (uint32_t)ctx->s_split_mode;
+        else if (n >= 3 && max_l >= 32768u && ctx->opts.haplotypes) {
+            uint32_t multi = 0;
+            const uint32_t pick[3] = {0u, n / 2u, n - 1u};
+            for (uint32_t k = 0; k < 3; ++k) {
+                const char *t = b.mm + b.mm_off[pick[k]];
+                const uint32_t len = b.mm_len[pick[k]];
+                const void *first = len ? memchr(t, ';', len) : nullptr;
+                if (first && (const char *)first + 1 < t + len) ++multi;            // text after the first block's ';'
+            }
+            s.s_split = multi >= 2 ? 1u : 0u;
+        }
         s.s_arena = (uint32_t)((sizeof(SFixed) + 15) & ~(size_t)15);
         s.s_setup_flex = 256;                      // stream mode: k_flat_setup writes the CIGAR table straight into the pool
         uint64_t need_s = 0;
@@ -520,9 +538,10 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         const unsigned rgrid = (unsigned)std::min<uint64_t>(((uint64_t)n + kFThreads / 32 - 1) / (kFThreads / 32), (uint64_t)ctx->sm_count * 16);
         MMC_LAUNCH_SMEM(k_flat_setup, rgrid, (unsigned)kFThreads, (size_t)kWHeadBytes + (size_t)setup_arena * (kFThreads / 32), s.stream, P, F);
         CU(ctx, cudaGetLastError());
-        StreamParams SP; SP.arena_bytes = s.s_arena; SP.head_bytes = ctx->s_head;
+        StreamParams SP; SP.arena_bytes = s.s_arena; SP.head_bytes = ctx->s_head; SP.split = s.s_split; SP.pad_ = 0;
         PreParams Q; Q.reads = s.d_reads; Q.n = n;
-        const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n + kSThreads / 32 - 1) / (kSThreads / 32), (uint64_t)ctx->sm_count * s.s_ctas));
+        const uint64_t units = (uint64_t)n * (s.s_split ? 2u : 1u);
+        const unsigned sgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((units + kSThreads / 32 - 1) / (kSThreads / 32), (uint64_t)ctx->sm_count * s.s_ctas));
         const size_t ssmem = (size_t)ctx->s_head + (size_t)s.s_arena * (kSThreads / 32);
         if (s.s_ctas == 8) MMC_LAUNCH_SMEM((k_decode_stream<8>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
         else if (s.s_ctas == 6) MMC_LAUNCH_SMEM((k_decode_stream<6>), sgrid, (unsigned)kSThreads, ssmem, s.stream, P, SP, Q);
@@ -681,6 +700,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
         else if (!strcmp(e, "stream")) ctx->stream_path = 2;          // always (default 1: per batch, by the reads' shape)
     }
+    if (const char *e = getenv("MMC_STREAM_SPLIT")) { const int v = atoi(e); if (v == 0 || v == 1) ctx->s_split_mode = v; }   // test hook / A-B timing
     if (const char *e = getenv("MMC_STREAM_MINB")) { int v = atoi(e); if (v == 8 || v == 6 || v == 5 || v == 4) ctx->s_minb = v; }   // tuning
     ctx->s_head = (uint32_t)std::min<int>(opts->n_mods, kWLutSlots) * 256u;
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning

@@ -63,6 +63,8 @@ __device__ __forceinline__ SArena s_arena(uint32_t aoff) {
 struct StreamParams {
     uint32_t arena_bytes;                    // per warp, multiple of 16, >= sizeof(SFixed) + 256
     uint32_t head_bytes;                     // call LUTs in front of the arenas
+    uint32_t split;                          // work unit = (read, even / odd blocks) instead of a read: half as many reads in flight
+    uint32_t pad_;
 };
 
 __device__ __forceinline__ uint32_t s_flags(uint32_t u, uint32_t mode, uint32_t pat) {
@@ -443,10 +445,16 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
         if (lane == 0) r = atomicAdd(P.work_counter, 1u);
         r = __shfl_sync(kFull, r, 0);
         __syncwarp();
+        // split mode: the blocks of a read stream SEQ independently (their first ML index comes from k_flat_setup), so two
+        // warps take the even and the odd blocks of the same read at the same time.  Long reads with several strata per cell
+        // (config 4: 50 kb, 128 bytes of cells per position) then keep half as many reads -- half the window of the count
+        // arrays -- in flight for the same number of warps, which is what the L2 can hold.
+        const uint32_t half = W.split ? (r & 1u) : 0u, stride = W.split ? 2u : 1u;
+        if (W.split) r >>= 1;
         if (r >= Q.n) break;
         const WRead *G = &Q.reads[r];
         const uint32_t nb = G->st.n_blocks;
-        if (nb == 0u) continue;                                    // deferred or fatal in k_flat_setup
+        if (nb <= half) continue;                                  // deferred or fatal in k_flat_setup (0 blocks), or no block for this half
         {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(G);
             uint32_t *dst = reinterpret_cast<uint32_t *>(R);
@@ -459,8 +467,9 @@ __global__ void __launch_bounds__(kSThreads, MINB) k_decode_stream(const __grid_
         const uint32_t n_blocks = S.n_blocks;
         uint32_t ml_base = 0, err = 0;
         const bool ex = P.insertions || P.haplotypes || S.cshift != 0u;
-        for (uint32_t jb = 0; jb < n_blocks; ++jb) {
+        for (uint32_t jb = half; jb < n_blocks; jb += stride) {
             const WBlock *bd = &R->blk[jb];
+            if (W.split) ml_base = bd->ml_base;
             const uint32_t a0 = bd->hdr_end, a1 = bd->end;
             const uint32_t tail = !w_fast_ok(P, S, bd) ? 4u : (bd->cls == 0u ? 1u : 0u) + (ex ? 2u : 0u);
             s_open_block(aoff, jb, lane);

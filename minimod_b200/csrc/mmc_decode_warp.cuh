@@ -622,6 +622,42 @@ __device__ __forceinline__ bool w_needs_bitmap(const WBlock *bd) { return bd->an
 // ---------------------------------------------------------------------------------------
 //   flex_words   capacity of the arena that will hold dir|cq|cr + index + bitmap (decides the sampling shifts)
 //   local_words  capacity of THIS arena for dir|cq|cr (k_flat_setup's arenas are smaller than the consumer's)
+// First ML index of every block (src/mod.c:1200: ml_start_idx advances by tokens x codes block after block), without decoding
+// the skip counts: the tokens of a block are counted with the token-start definition of w_tile_ranks (a byte of the block's
+// list that follows a ',' -- or is the list's first byte -- and is not a ',' itself).  Lets the blocks of one read be decoded
+// by different warps (k_decode_stream, split mode).  Warp-wide; blocks 1.. get bd->ml_base, block 0 keeps 0.
+__device__ __noinline__ void w_block_ml_bases(WRead *R, uint32_t lane) {
+    const WState &S = R->st;
+    const uint8_t *mm = S.mm;
+    const uint32_t mm_len = S.mm_len, n_blocks = S.n_blocks;
+    uint32_t acc = 0;
+    for (uint32_t j = 0; j + 1u < n_blocks; ++j) {
+        const uint32_t a0 = R->blk[j].hdr_end, a1 = R->blk[j].end, K = R->blk[j].K;
+        uint32_t cnt = 0, carry_bit = 0;                                            // carry_bit: the byte before this step's first chunk is ','
+        for (uint32_t base = a0 & ~15u; base < a1; base += 512u) {
+            const uint32_t p0 = base + lane * 16u;
+            uint32_t cm = 0;
+            if (p0 < a1 && p0 < mm_len) cm = byte_mask16(ld16(mm + p0), ',');
+            uint32_t pbit = (__shfl_up_sync(kFull, cm, 1) >> 15) & 1u;
+            if (lane == 0) pbit = carry_bit;
+            uint32_t st = ((cm << 1) | pbit) & ~cm & 0xffffu;
+            uint32_t lo_b = a0 > p0 ? a0 - p0 : 0u, hi_b = a1 > p0 ? a1 - p0 : 0u;
+            if (lo_b > 16u) lo_b = 16u;
+            if (hi_b > 16u) hi_b = 16u;
+            if (a0 >= p0 && a0 < p0 + 16u && !((cm >> lo_b) & 1u)) st |= 1u << lo_b;
+            st &= ~((1u << lo_b) - 1u);
+            st &= (1u << hi_b) - 1u;
+            cnt += (uint32_t)__popc(st);
+            carry_bit = (__shfl_sync(kFull, cm, 31) >> 15) & 1u;
+        }
+        const uint32_t tokens = __shfl_sync(kFull, warp_incl_scan(cnt, lane), 31);
+        if (tokens > 0u) acc += tokens * K;
+        __syncwarp();
+        if (lane == 0) R->blk[j + 1u].ml_base = acc;
+    }
+    __syncwarp();
+}
+
 template <bool TILE>
 __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, uint32_t flex_words, uint32_t local_words,
                                           uint32_t *defer_list, uint32_t *defer_n, uint32_t r, uint32_t lane, const FlatAlloc *stream = nullptr) {
@@ -740,6 +776,8 @@ __device__ __noinline__ bool w_setup_read(const DecodeParams &P, uint32_t aoff, 
             if ((bm_mask >> b) & 1u) bd.o_bm = next;
         }
     }
+
+    if (stream && n_blocks > 1u && !herr_mask) { __syncwarp(); w_block_ml_bases(R, lane); }
 
     // ---- CIGAR prefix sums == get_aln() (src/mod.c:811-880)
     uint32_t carry_q = 0, carry_r = 0, big = 0;

@@ -57,3 +57,14 @@ def test_sparse_rows_sorted_on_device(emul_lib, monkeypatch, name):
     case = [c for c in GOLDEN_CASES if c[0] == name][0]
     out = run_case(emul_lib, *case[1:])
     assert sorted_lines(out) == sorted_lines(golden_bytes(name))
+
+
+@pytest.mark.parametrize("name", ["test8.tsv", "test12.tsv", "test11.tsv", "test5a.tsv", "test16.tsv", "test2c_wild.tsv"])
+def test_split_blocks_agree(emul_lib, monkeypatch, name):
+    """k_decode_stream, split mode: the even and the odd MM blocks of a read are decoded by different warps, each block's
+    first ML index (src/mod.c:1200) precomputed by k_flat_setup from the token counts of the blocks before it."""
+    monkeypatch.setenv("MMC_DECODE_PATH", "stream")
+    monkeypatch.setenv("MMC_STREAM_SPLIT", "1")
+    case = [c for c in GOLDEN_CASES if c[0] == name][0]
+    out = run_case(emul_lib, *case[1:])
+    assert sorted_lines(out) == sorted_lines(golden_bytes(name))

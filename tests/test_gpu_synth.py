@@ -45,6 +45,17 @@ def test_synthetic_parity_cuda_paths(cuda_lib, monkeypatch, path, arena, config,
     assert n > 0
 
 
+@pytest.mark.parametrize("sub", ["freq", "view"])
+@pytest.mark.parametrize("config,cov", [(3, 2.0), (6, 1.5), (4, 0.5), (2, 2.0)])
+def test_synthetic_parity_cuda_split_blocks(cuda_lib, monkeypatch, config, cov, sub):
+    """k_decode_stream with the even and the odd MM blocks of a read on different warps (first ML index of every block from
+    k_flat_setup): two-block reads (configs 3, 4, 6), one-block reads (config 2: the odd work unit is a no-op)."""
+    monkeypatch.setenv("MMC_DECODE_PATH", "stream")
+    monkeypatch.setenv("MMC_STREAM_SPLIT", "1")
+    n, st = run_synth(cuda_lib, config, 1000000, cov, sub)
+    assert n > 0
+
+
 @pytest.mark.parametrize("config,cov", [(3, 3.0), (6, 2.0)])
 def test_synthetic_parity_cuda_sparse_on_device(cuda_lib, monkeypatch, config, cov):
     """--insertions (config 3) and haplotype (config 6) rows with the sparse side buffer sorted / reduced / merged
