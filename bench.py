@@ -333,6 +333,10 @@ def measure(env, config, synth, steps, warmup, first=0, count=None, shard_note=N
     wall = t1 - t0
     dev_s = sum(kernel_ms) / 1e3
 
+    # the table of exactly ONE pass for what follows (the sparse side buffer holds a record per call outside the dense cells, so
+    # its finalize would otherwise be timed on warmup + K passes' worth of records)
+    env.chk(ctxA, lib.mmc_freq_reset(ctxA))
+    env.chk(ctxA, lib.mmc_batch_launch(ctxA, bA)); env.chk(ctxA, lib.mmc_sync(ctxA))
     halo_res = None
     if halo is not None:                                   # region sharding: move the boundary counts to their owners
         halo_res = halo(ctxA)

@@ -100,7 +100,8 @@ struct mmc_ctx {
     int stream_path = 1;                       // k_flat_setup + k_decode_stream (default): streaming merge, constant shared memory per warp
     uint32_t s_head = 256;                     // k_decode_stream: bytes of call LUTs in front of the arenas
     int s_minb = 6;                            // k_decode_stream<MINB>: resident CTAs per SM the registers are bounded for (MMC_STREAM_MINB)
-    int s_split_mode = -1;                     // -1: per batch (long reads with several MM blocks and haplotype strata); 0 / 1: MMC_STREAM_SPLIT
+    int s_split_mode = 0;                      // MMC_STREAM_SPLIT: 1 = (read, even / odd blocks) work units, -1 = per batch (long reads with
+                                               // several MM blocks and haplotype strata).  Off by default: measured neutral
     int split_path = 1;                        // k_flat_setup + k_decode_warp<PRE>: setup split from the fused kernel
     int warp_path = 1;                         // then k_decode_warp, then k_decode for what that defers
     // k_decode_warp<MINB>: variants bounded for MINB resident CTAs per SM; the arena of a warp shrinks as MINB grows.
@@ -700,7 +701,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
         else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
         else if (!strcmp(e, "stream")) ctx->stream_path = 2;          // always (default 1: per batch, by the reads' shape)
     }
-    if (const char *e = getenv("MMC_STREAM_SPLIT")) { const int v = atoi(e); if (v == 0 || v == 1) ctx->s_split_mode = v; }   // test hook / A-B timing
+    if (const char *e = getenv("MMC_STREAM_SPLIT")) { const int v = atoi(e); if (v >= -1 && v <= 1) ctx->s_split_mode = v; }   // test hook / A-B timing
     if (const char *e = getenv("MMC_STREAM_MINB")) { int v = atoi(e); if (v == 8 || v == 6 || v == 5 || v == 4) ctx->s_minb = v; }   // tuning
     ctx->s_head = (uint32_t)std::min<int>(opts->n_mods, kWLutSlots) * 256u;
     if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
