@@ -381,6 +381,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         }
     };
 
+    double t_release = 0, t_acquire = 0, t_submit = 0, t_drain = 0, t_view = 0;   // MINIMOD_TRACE: where the main loop's wall clock goes
     int more = 1;
     while (more) {
         int d = 0;
@@ -392,12 +393,15 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         mmc_ctx *c = ctxs[d];
         Ring &rg = rings[d];
         const int si = rg.next; rg.next = (rg.next + 1) % n_slots;
+        double tr0 = realtime();
         if (rg.b[si]) {                                   // recycle the oldest slot (joins the "previous processor")
             if (mmc_batch_release(c, rg.b[si]) != MMC_OK) die_read(c, rg.meta[si]);
             rg.b[si] = nullptr;
         }
+        t_release += realtime() - tr0; tr0 = realtime();
         mmc_batch_t *b = nullptr;
         if (mmc_batch_acquire(c, &b) != MMC_OK) { ERROR("%s", mmc_strerror(c)); exit(EXIT_FAILURE); }
+        t_acquire += realtime() - tr0;
         double t0 = realtime();
         more = loader.fill(b, &rg.meta[si], &err);
         load_time += realtime() - t0;
@@ -405,7 +409,9 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         const BatchStats &st = rg.meta[si].stats;
         fprintf(stderr, "[%s::%.3f*%.2f] %d Entries (%.1fM bases) loaded\n", func, realtime() - realtime0,
                 cputime() / (realtime() - realtime0), st.n_recs, st.processed_bytes / (1000.0 * 1000.0));
+        tr0 = realtime();
         if (mmc_batch_submit(c, b) != MMC_OK) { ERROR("%s", mmc_strerror(c)); exit(EXIT_FAILURE); }
+        t_submit += realtime() - tr0; tr0 = realtime();
         rg.b[si] = b;
         if (stream_rows && b->n_reads && b->tid[0] >= 0) {
             // the batches submitted before this one hold every read that starts before its first read
@@ -418,6 +424,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
             rows_early += n; rows_total += n;
             fmt_push(c, recs, n);
         }
+        t_drain += realtime() - tr0;
         if (subtool == MMC_VIEW) {
             const mmc_view_rec_t *recs = nullptr; uint64_t n = 0;
             if (mmc_view_fetch(c, b, &recs, &n) != MMC_OK) die_read(c, rg.meta[si]);
@@ -443,6 +450,9 @@ static int run_tool(int subtool, int argc, char *argv[]) {
             if (rings[d].b[i] && mmc_batch_release(ctxs[d], rings[d].b[i]) != MMC_OK) die_read(ctxs[d], rings[d].meta[i]);
 
     stamp("last batch submitted and released");
+    if (trace) fprintf(stderr, "[trace] main loop: fill %.3f s, slot release (waits for the slot's batch) %.3f s, acquire %.3f s, submit %.3f s, drain %.3f s\n",
+                       load_time, t_release, t_acquire, t_submit, t_drain);
+    (void)t_view;
     double sort_time = 0, halo_ms = 0;
     uint64_t halo_bytes = 0;
     if (stream_rows) {

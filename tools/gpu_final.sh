@@ -24,9 +24,17 @@ print("clocks", d.get("clocks"))
 PY
       ;;
     profiles)
+      # (the reports are ~20 MB each and gpurun brings back 64 MB: they are summarised here and only config 5's is kept)
+      declare -A READS=([2]=99616 [3]=149425 [4]=29885 [5]=409850)
       for c in 5 2 3 4; do
-        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_decode_stream|k_flat_setup|k_decode_warp" -c 3 -o gpurun_out/${TAG}_prof_c$c -f \
+        rep=gpurun_out/${TAG}_prof_c$c
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_decode_stream|k_flat_setup|k_decode_warp" -c 2 -o $rep -f \
           python bench.py --config $c --only --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_c$c.log 2>&1; echo "ncu c$c rc=$?"
+        python tools/ncu_kernel_table.py $rep.ncu-rep > gpurun_out/${TAG}_ncu_kernels_config$c.txt 2>&1
+        python tools/ncu_l2_atomics.py $rep.ncu-rep > gpurun_out/${TAG}_ncu_l2_config$c.txt 2>&1
+        python tools/ncu_lines_by_file.py $rep.ncu-rep 1.0 "k_decode_stream|k_decode_warp" > gpurun_out/${TAG}_ncu_hot_lines_config$c.txt 2>&1
+        TRAFFIC_JSON=gpurun_out/${TAG}_traffic.json python tools/ncu_traffic.py $c:$rep.ncu-rep:${READS[$c]} > /dev/null 2>&1
+        [ $c != 5 ] && rm -f $rep.ncu-rep
       done
       for c in 5 3; do
         timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_c$c.csv \

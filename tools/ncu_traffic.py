@@ -4,7 +4,7 @@ stage's kernels (k_flat_setup + the decode kernel), per launch of the whole shar
 usage: ncu_traffic.py config:report.ncu-rep:reads ..."""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-path = os.path.join(ROOT, "profiles", "traffic.json")
+path = os.environ.get("TRAFFIC_JSON", os.path.join(ROOT, "profiles", "traffic.json"))
 try:
     out = json.load(open(path))
 except Exception:
