@@ -14,6 +14,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -337,11 +338,13 @@ static int run_tool(int subtool, int argc, char *argv[]) {
     // (--shard-regions, a BAM that turns out not to be sorted) is read back and formatted after the last batch as before.
     const bool stream_rows = subtool == MMC_FREQ && big_tid < 0 && !getenv("MINIMOD_NO_DRAIN");
     struct FmtJob { std::vector<mmc_freq_rec_t> rows; std::vector<std::string> codes; };
-    std::vector<std::string> contig_text(stream_rows ? n_contigs : 0);
+    std::vector<std::vector<std::string>> contig_text(stream_rows ? n_contigs : 0);   // per contig: pieces of text in row order
     std::deque<FmtJob> fmt_queue;
     std::mutex fmt_mu;
     std::condition_variable fmt_cv;
     bool fmt_done = false;
+    uint64_t fmt_pushed = 0;                              // jobs handed to the worker (main thread) / jobs it has finished
+    std::atomic<uint64_t> fmt_finished(0);
     uint64_t rows_early = 0, rows_total = 0;
     double fmt_secs = 0;
     std::thread fmt_thread;
@@ -360,10 +363,12 @@ static int run_tool(int subtool, int argc, char *argv[]) {
             for (uint64_t i = 0; i < n;) {
                 uint64_t j = i;
                 while (j < n && job.rows[j].tid == job.rows[i].tid) ++j;
-                format_freq_rows(&contig_text[job.rows[i].tid], oo, bam.names[job.rows[i].tid], job.rows.data(), i, j, job.codes);
+                contig_text[job.rows[i].tid].emplace_back();
+                format_freq_rows(&contig_text[job.rows[i].tid].back(), oo, bam.names[job.rows[i].tid], job.rows.data(), i, j, job.codes);
                 i = j;
             }
             fmt_secs += realtime() - t0;
+            fmt_finished.fetch_add(1, std::memory_order_release);
         }
     });
     auto fmt_push = [&](mmc_ctx *c, const mmc_freq_rec_t *r, uint64_t n) {
@@ -372,13 +377,11 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         job.rows.assign(r, r + n);                        // out of the library's alternating pinned buffers
         job.codes = code_names_of(c);
         { std::lock_guard<std::mutex> lk(fmt_mu); fmt_queue.push_back(std::move(job)); }
+        ++fmt_pushed;
         fmt_cv.notify_one();
     };
-    auto fmt_idle = [&]() {                               // every queued job formatted
-        for (;;) {
-            { std::lock_guard<std::mutex> lk(fmt_mu); if (fmt_queue.empty()) break; }
-            std::this_thread::yield();
-        }
+    auto fmt_idle = [&]() {                               // every job handed over so far is formatted: contig_text is the caller's
+        while (fmt_finished.load(std::memory_order_acquire) != fmt_pushed) std::this_thread::yield();
     };
 
     double t_release = 0, t_acquire = 0, t_submit = 0, t_drain = 0, t_view = 0;   // MINIMOD_TRACE: where the main loop's wall clock goes
@@ -466,16 +469,43 @@ static int run_tool(int subtool, int argc, char *argv[]) {
                 WARNING("%s", "reads are not in coordinate order: the rows written out early are discarded and the table is rebuilt at the end");
                 fmt_idle();
                 { std::lock_guard<std::mutex> lk(fmt_mu); }
-                for (int t = 0; t < n_contigs; ++t) if (owner[t] == d) std::string().swap(contig_text[t]);
+                for (int t = 0; t < n_contigs; ++t) if (owner[t] == d) std::vector<std::string>().swap(contig_text[t]);
                 rows_total = 0; rows_early = 0;           // (reported figures only)
                 if (mmc_freq_undrain(ctxs[d]) != MMC_OK) { ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE); }
                 rc = mmc_freq_finalize(ctxs[d], &recs, &n);
             }
             if (rc != MMC_OK) { ERROR("%s", mmc_strerror(ctxs[d])); exit(EXIT_FAILURE); }
             rows_total += n;
-            fmt_push(ctxs[d], recs, n);
+            sort_time += realtime() - s0;
+            // what is left (everything, when nothing could leave early: --insertions, unsorted input) is formatted by -t threads:
+            // chunks of rows that stay inside a contig, claimed by an atomic counter, their text kept in row order
+            const double o1 = realtime();
+            fmt_idle();
+            { std::lock_guard<std::mutex> lk(fmt_mu); }                     // (the worker is between jobs: contig_text is ours)
+            struct Chunk { int32_t tid; uint64_t b, e; std::string text; };
+            std::vector<Chunk> chunks;
+            const uint64_t per = 1u << 18;
+            for (uint64_t i = 0; i < n;) {
+                uint64_t j = i;
+                while (j < n && j - i < per && recs[j].tid == recs[i].tid) ++j;
+                chunks.push_back({recs[i].tid, i, j, std::string()});
+                i = j;
+            }
+            const std::vector<std::string> cn = code_names_of(ctxs[d]);
+            std::atomic<size_t> next_chunk(0);
+            auto work = [&]() {
+                for (size_t k; (k = next_chunk.fetch_add(1)) < chunks.size();)
+                    format_freq_rows(&chunks[k].text, oo, bam.names[chunks[k].tid], recs, chunks[k].b, chunks[k].e, cn);
+            };
+            std::vector<std::thread> pool;
+            const int nt = (int)std::min<size_t>((size_t)std::max(1, opt.num_thread), chunks.size());
+            for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+            work();
+            for (std::thread &t : pool) t.join();
+            for (Chunk &ck : chunks) contig_text[ck.tid].push_back(std::move(ck.text));
+            output_time += realtime() - o1;
+            s0 = realtime();
         }
-        sort_time = realtime() - s0;
         double o0 = realtime();
         { std::lock_guard<std::mutex> lk(fmt_mu); fmt_done = true; }
         fmt_cv.notify_all();
@@ -483,7 +513,7 @@ static int run_tool(int subtool, int argc, char *argv[]) {
         std::vector<int> order(n_contigs);
         for (int i = 0; i < n_contigs; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return strcmp(bam.names[a].c_str(), bam.names[b].c_str()) < 0; });
-        for (int t : order) if (!contig_text[t].empty()) fwrite(contig_text[t].data(), 1, contig_text[t].size(), opt.out);
+        for (int t : order) for (const std::string &piece : contig_text[t]) fwrite(piece.data(), 1, piece.size(), opt.out);
         output_time += realtime() - o0;
     } else if (subtool == MMC_FREQ) {
         double s0 = realtime();
