@@ -143,6 +143,8 @@ struct mmc_ctx {
     std::vector<uint32_t> drained_to;                              // per contig: positions below this were returned by a drain
     uint32_t wm_tid = 0, wm_pos = 0; bool wm_set = false;          // watermark of the last drain that returned rows
     bool drain_violated = false;                                   // a batch uploaded after a drain starts before its watermark
+    unsigned long long sparse_lo = 0;                              // side-buffer records with a major key below this were returned by a drain
+    double host_upload_ms = 0, host_launch_ms = 0; bool trace_host = false;   // MMC_TRACE_CREATE: host time inside mmc_batch_submit
     cudaEvent_t ev_reset = nullptr; bool reset_pending = false;    // mmc_freq_reset() clears on fin_stream; the next decode launches wait for it on the device
     std::vector<int32_t> reset_touch;                              // (source of its asynchronous copy)
     mmc_freq_rec_t *h_drain[2] = {nullptr, nullptr}; size_t h_drain_cap[2] = {0, 0}; int drain_flip = 0;   // pinned, alternating
@@ -450,6 +452,7 @@ int reserve_sparse(mmc_ctx *ctx, const Slot &s) {
     CU(ctx, cudaMemcpy(&sn, ctx->d_sparse_n, 8, cudaMemcpyDeviceToHost));
     if (sn > ctx->sparse_cap) sn = ctx->sparse_cap;
     if (sn) CU(ctx, cudaMemcpy(nb, ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToDevice));
+    CU(ctx, cudaMemset(nb + sn, 0xff, sizeof(SparseRec) * (cap - sn)));
     CU(ctx, cudaFree(ctx->d_sparse));
     ctx->d_sparse = nb; ctx->sparse_cap = cap;
     return MMC_OK;
@@ -522,8 +525,9 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
             CU(ctx, cudaStreamSynchronize(s.stream));
             if (s.d_pool) CU(ctx, cudaFree(s.d_pool));
             s.d_pool = nullptr; s.pool_words = 0;
-            CU(ctx, cudaMalloc((void **)&s.d_pool, pool_need * 4));
-            s.pool_words = pool_need;
+            const uint64_t want = pool_need + pool_need / 4;   // headroom: batches differ by a few per cent, every regrowth is a device-wide synchronisation
+            CU(ctx, cudaMalloc((void **)&s.d_pool, want * 4));
+            s.pool_words = want;
         }
         F.reads = s.d_reads;
         F.fa.pool = s.d_pool; F.fa.cursor = s.d_state + 4; F.fa.cap = s.pool_words;
@@ -820,6 +824,7 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     // ---- side buffers
     ctx->sparse_cap = o.sparse_capacity ? o.sparse_capacity : (o.subtool == MMC_FREQ ? std::max<uint64_t>(1u << 20, o.max_bytes / 8) : 16);   // starting size: grows (reserve_sparse)
     CUC(cudaMalloc((void **)&ctx->d_sparse, sizeof(SparseRec) * ctx->sparse_cap));
+    CUC(cudaMemset(ctx->d_sparse, 0xff, sizeof(SparseRec) * ctx->sparse_cap));   // sentinels: a slot nobody has written is skipped
     CUC(cudaMalloc((void **)&ctx->d_sparse_n, 8));
     CUC(cudaMemset(ctx->d_sparse_n, 0, 8));
     ctx->view_cap = o.view_capacity ? o.view_capacity : std::max<uint64_t>(1u << 16, o.max_bytes);
@@ -850,6 +855,9 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
 void mmc_destroy(mmc_ctx *ctx) {
     MMC_DEV(ctx);
     if (!ctx) return;
+    if (getenv("MMC_TRACE_CREATE"))
+        fprintf(stderr, "[mmc_destroy] host time inside mmc_batch_submit: %.1f ms enqueuing copies / unpack kernels + batch analysis, %.1f ms launching the decode stage (scratch growth included)\n",
+                ctx->host_upload_ms, ctx->host_launch_ms);
     cudaDeviceSynchronize();
     for (Slot &s : ctx->slots) {
         if (s.h_arena) cudaFreeHost(s.h_arena);
@@ -1046,9 +1054,15 @@ int mmc_batch_submit(mmc_ctx *ctx, mmc_batch_t *batch) {
     if (!ctx->committed) return fail(ctx, MMC_ESTATE, "mmc_batch_submit: call mmc_ref_commit() first");
     int rc = wait_slot(ctx, *s);
     if (rc != MMC_OK) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
     rc = upload(ctx, *s);
     if (rc != MMC_OK) return rc;
-    return launch_decode(ctx, *s);
+    const auto t1 = std::chrono::steady_clock::now();
+    rc = launch_decode(ctx, *s);
+    const auto t2 = std::chrono::steady_clock::now();
+    ctx->host_upload_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    ctx->host_launch_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+    return rc;
 }
 
 int mmc_batch_wait(mmc_ctx *ctx, mmc_batch_t *batch) {
@@ -1133,7 +1147,7 @@ static int exclusive_sum(mmc_ctx *ctx, const uint32_t *in, uint32_t *out, uint32
 
 // Sort + reduce the sn records of the sparse side buffer into ctx->d_srows (row order), count into ctx->h_sn_rows
 // (valid after the next synchronize of fin_stream).  Everything is queued on fin_stream.
-static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn) {
+static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn, unsigned long long key_lo, unsigned long long key_hi) {
     const uint32_t n = (uint32_t)sn;
     size_t tmp_bytes = 0;
 #ifndef MMC_EMUL
@@ -1176,15 +1190,15 @@ static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn) {
     MMC_LAUNCH(k_sparse_keys, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, n, k32a, ia);
     CU(ctx, cudaGetLastError());
     if ((rc = sort_pairs<uint32_t>(ctx, k32a, k32b, ia, ib, n, 25, tmp, tmp_bytes)) != MMC_OK) return rc;
-    MMC_LAUNCH(k_sparse_gather, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ib, n, k64a);
+    MMC_LAUNCH(k_sparse_gather, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ib, n, k64a, key_lo, key_hi);
     CU(ctx, cudaGetLastError());
     if ((rc = sort_pairs<unsigned long long>(ctx, k64a, k64b, ib, ia, n, std::min(64, 41 + tid_bits), tmp, tmp_bytes)) != MMC_OK) return rc;
     uint32_t *flag = k32a, *off = k32b;                                      // the minor keys are no longer needed
-    MMC_LAUNCH(k_sparse_heads, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ia, n, flag);
+    MMC_LAUNCH(k_sparse_heads, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ia, n, flag, key_lo, key_hi);
     CU(ctx, cudaGetLastError());
     if ((rc = exclusive_sum(ctx, flag, off, n, tmp, tmp_bytes)) != MMC_OK) return rc;
     MMC_LAUNCH(k_sparse_emit, grid, (unsigned)kSpThreads, ctx->fin_stream, (const SparseRec *)ctx->d_sparse, (const uint32_t *)ia, (const uint32_t *)flag,
-               (const uint32_t *)off, n, ctx->d_srows, ctx->d_sn_rows);
+               (const uint32_t *)off, n, ctx->d_srows, ctx->d_sn_rows, key_lo, key_hi);
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(ctx->h_sn_rows, ctx->d_sn_rows, 8, cudaMemcpyDeviceToHost, ctx->fin_stream));
     ctx->tm.kernel_launches += 4;
@@ -1195,9 +1209,13 @@ static int sparse_rows_on_device(mmc_ctx *ctx, uint64_t sn) {
 // for every batch).  drain == true: what lies before the watermark (wm_tid, wm_pos), after waiting only for the batches
 // that hold a read starting before it -- later batches keep copying and decoding while these rows are compacted and read
 // back (they only touch cells at or after the watermark).
-static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_pos, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
+static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_pos_given, const mmc_freq_rec_t **recs, uint64_t *n_recs) {
     int rc = MMC_OK;
-    const uint64_t wm_key = ((uint64_t)wm_tid << 32) | wm_pos;
+    const uint64_t wm_key = ((uint64_t)wm_tid << 32) | wm_pos_given;
+    // Rows leave up to ONE POSITION BELOW the watermark: a read that starts exactly at the watermark may still add a side-buffer
+    // record at the position before it (the left flank of a leading insertion, src/mod.c:1122-1127), and all rows of a position
+    // -- dense cells and side-buffer records -- have to leave in the same call to come out in order.
+    const uint32_t wm_pos = wm_pos_given ? wm_pos_given - 1u : 0u;
     if (!drain) rc = mmc_sync(ctx);
     else for (Slot &s : ctx->slots) {
         if (!s.in_flight || ((((uint64_t)s.min_tid << 32) | s.min_pos) >= wm_key && s.n_reads_submitted)) continue;
@@ -1240,8 +1258,16 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
     if (sn > ctx->sparse_cap)
         return fail(ctx, MMC_ENOMEM, "sparse count buffer overflow (%llu records > capacity %llu); raise sparse_capacity",
                     sn, (unsigned long long)ctx->sparse_cap);
-    if (drain && sn > 0) return MMC_OK;        // records of the side buffer are not partitioned by position: left to mmc_freq_finalize()
-    const bool dev_sparse = sn > 0 && sn >= ctx->sparse_dev_min && sn < 0x7fffffffull;   // many records (--insertions): sorted on the device
+    // Which records of the side buffer this call owes: major keys in [sparse_lo, sparse_hi).  Batches in flight may be
+    // appending while a drain reads the buffer: their keys are never below sparse_hi, and what they have not written yet
+    // reads as sentinels (the buffer is pre-filled with them).
+    unsigned long long sparse_hi = ~0ull;
+    if (drain) {
+        sparse_hi = ((unsigned long long)wm_tid << 41) | ((unsigned long long)wm_pos << 9);
+        if (sparse_hi < ctx->sparse_lo) sparse_hi = ctx->sparse_lo;
+    }
+    if (drain && sn >= 0x7fffffffull) return MMC_OK;         // (too many records for one device pass: left to mmc_freq_finalize())
+    const bool dev_sparse = sn > 0 && (drain || sn >= ctx->sparse_dev_min) && sn < 0x7fffffffull;   // many records (--insertions), or a drain: sorted on the device
     std::vector<SparseRec> raw(dev_sparse ? 0 : sn);
     if (sn && !dev_sparse) {
         CU(ctx, cudaMemcpyAsync(raw.data(), ctx->d_sparse, sizeof(SparseRec) * sn, cudaMemcpyDeviceToHost, ctx->fin_stream));
@@ -1259,7 +1285,7 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
     uint64_t n_dense = 0;
     CU(ctx, cudaEventRecord(ctx->ev_f0, ctx->fin_stream));
     if (dev_sparse) {
-        rc = sparse_rows_on_device(ctx, sn);
+        rc = sparse_rows_on_device(ctx, sn, ctx->sparse_lo, sparse_hi);
         if (rc != MMC_OK) return rc;
         if (!tiles) CU(ctx, cudaStreamSynchronize(ctx->fin_stream));       // (else the wait for the tile totals covers it)
     }
@@ -1366,6 +1392,8 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
     const bool fin_trace = getenv("MMC_TRACE_FINALIZE") != nullptr;
     const auto t_s0 = std::chrono::steady_clock::now();
     if (!raw.empty()) {
+        CU(ctx, cudaStreamSynchronize(ctx->fin_stream));   // (the copy of the records)
+        for (SparseRec &r : raw) if (r.a < ctx->sparse_lo || r.a >= sparse_hi) r.a = kSpSentinel;   // not this call's (see above)
         std::sort(raw.begin(), raw.end(), [](const SparseRec &x, const SparseRec &y) {
             if (x.a != y.a) return x.a < y.a;                 // tid, pos, strand, code == numeric order of a
             uint32_t xi = x.b & 0xffffu, yi = y.b & 0xffffu;
@@ -1437,9 +1465,10 @@ static int finalize_rows(mmc_ctx *ctx, bool drain, uint32_t wm_tid, uint32_t wm_
     *n_recs = n_dense + ns;
     *recs = *n_recs ? h_rows : nullptr;
     if (drain) {                                              // what this call returned is never returned again
+        ctx->sparse_lo = sparse_hi;
         for (size_t i = 0; i < nc && (uint32_t)i <= wm_tid; ++i)
             ctx->drained_to[i] = std::max(ctx->drained_to[i], (uint32_t)i < wm_tid ? ctx->contigs[i].len : std::min(wm_pos, ctx->contigs[i].len));
-        if (!ctx->wm_set || wm_key > (((uint64_t)ctx->wm_tid << 32) | ctx->wm_pos)) { ctx->wm_tid = wm_tid; ctx->wm_pos = wm_pos; }
+        if (!ctx->wm_set || wm_key > (((uint64_t)ctx->wm_tid << 32) | ctx->wm_pos)) { ctx->wm_tid = wm_tid; ctx->wm_pos = wm_pos_given; }
         ctx->wm_set = true;
         ctx->drain_flip ^= 1;
     }
@@ -1472,7 +1501,7 @@ int mmc_freq_undrain(mmc_ctx *ctx) {
     MMC_DEV(ctx);
     if (!ctx) return MMC_EINVAL;
     ctx->drained_to.assign(ctx->contigs.size(), 0u);
-    ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false;
+    ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false; ctx->sparse_lo = 0;
     return MMC_OK;
 }
 
@@ -1496,13 +1525,15 @@ int mmc_freq_reset(mmc_ctx *ctx) {
     }
     if (nc) CU(ctx, cudaMemcpyAsync(ctx->d_touch, touch.data(), sizeof(int32_t) * 2 * nc, cudaMemcpyHostToDevice, ctx->fin_stream));
     CU(ctx, cudaMemsetAsync(ctx->d_sparse_n, 0, 8, ctx->fin_stream));
+    if (ctx->sparse_seen)                                  // slots that are not written read as sentinels (finalize_rows)
+        CU(ctx, cudaMemsetAsync(ctx->d_sparse, 0xff, sizeof(SparseRec) * std::min<uint64_t>(ctx->sparse_seen, ctx->sparse_cap), ctx->fin_stream));
     // asynchronous: the next batches' H2D copies overlap the clearing; their kernels (launch_decode) and every later
     // finalize / drain (same stream) are ordered behind it on the device
     CU(ctx, cudaEventRecord(ctx->ev_reset, ctx->fin_stream));
     ctx->reset_pending = true;
     ctx->sparse_seen = 0;
     ctx->drained_to.assign(nc, 0u);
-    ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false;
+    ctx->wm_set = false; ctx->wm_tid = 0; ctx->wm_pos = 0; ctx->drain_violated = false; ctx->sparse_lo = 0;
     return MMC_OK;
 }
 

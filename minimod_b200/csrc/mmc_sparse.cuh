@@ -31,6 +31,14 @@ __device__ __forceinline__ uint32_t sparse_minor(uint32_t b) {             // (i
     return ((b & 0xffffu) << 9) | (h9 == 256u ? 0u : h9 + 1u);
 }
 
+// A pass works on the records whose major key lies in [lo, hi): what a drain behind a coordinate watermark takes (lo = the
+// previous watermark, hi = this one) or what the final pass still owes (hi = all ones, which also excludes the sentinels).
+// Everything else -- records an earlier drain returned, records of batches still in flight (never below a watermark; they may
+// even be half written: the slots past the fill level and the unused slots of a warp's chunk hold sentinels) -- reads as a sentinel.
+__device__ __forceinline__ unsigned long long sparse_major(const SparseRec &r, unsigned long long lo, unsigned long long hi) {
+    return (r.a >= lo && r.a < hi) ? r.a : kSpSentinel;
+}
+
 __global__ void __launch_bounds__(kSpThreads) k_sparse_keys(const SparseRec *raw, uint32_t n, uint32_t *minor, uint32_t *idx) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         minor[i] = sparse_minor(raw[i].b);
@@ -38,22 +46,26 @@ __global__ void __launch_bounds__(kSpThreads) k_sparse_keys(const SparseRec *raw
     }
 }
 
-__global__ void __launch_bounds__(kSpThreads) k_sparse_gather(const SparseRec *raw, const uint32_t *idx, uint32_t n, unsigned long long *major) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) major[i] = raw[idx[i]].a;
+__global__ void __launch_bounds__(kSpThreads) k_sparse_gather(const SparseRec *raw, const uint32_t *idx, uint32_t n, unsigned long long *major,
+                                                              unsigned long long lo, unsigned long long hi) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) major[i] = sparse_major(raw[idx[i]], lo, hi);
 }
 
-// flag[i] = 1 when sorted record i starts a run of equal (a, b); the chunk sentinels (sorted last) never do
-__global__ void __launch_bounds__(kSpThreads) k_sparse_heads(const SparseRec *raw, const uint32_t *idx, uint32_t n, uint32_t *flag) {
+// flag[i] = 1 when sorted record i starts a run of equal (a, b); sentinels (sorted last) never do
+__global__ void __launch_bounds__(kSpThreads) k_sparse_heads(const SparseRec *raw, const uint32_t *idx, uint32_t n, uint32_t *flag,
+                                                             unsigned long long lo, unsigned long long hi) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const SparseRec r = raw[idx[i]];
-        uint32_t f = r.a != kSpSentinel;                                    // (no producer writes sentinels at present)
-        if (f && i > 0) { const SparseRec p = raw[idx[i - 1u]]; f = p.a != r.a || p.b != r.b; }
+        const unsigned long long ra = sparse_major(r, lo, hi);
+        uint32_t f = ra != kSpSentinel;
+        if (f && i > 0) { const SparseRec p = raw[idx[i - 1u]]; f = sparse_major(p, lo, hi) != ra || p.b != r.b; }
         flag[i] = f;
     }
 }
 
 __global__ void __launch_bounds__(kSpThreads) k_sparse_emit(const SparseRec *raw, const uint32_t *idx, const uint32_t *flag, const uint32_t *off,
-                                                            uint32_t n, FreqRecDev *rows, unsigned long long *n_rows) {
+                                                            uint32_t n, FreqRecDev *rows, unsigned long long *n_rows,
+                                                            unsigned long long lo, unsigned long long hi) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (i == n - 1u) *n_rows = (unsigned long long)off[i] + flag[i];
         if (!flag[i]) continue;
@@ -61,7 +73,7 @@ __global__ void __launch_bounds__(kSpThreads) k_sparse_emit(const SparseRec *raw
         unsigned long long called = r.w & 0xffffu, mod = r.w >> 16;
         for (uint32_t j = i + 1u; j < n && !flag[j]; ++j) {                // the rest of the run (short: one record per read)
             const SparseRec q = raw[idx[j]];
-            if (q.a == kSpSentinel) break;
+            if (sparse_major(q, lo, hi) == kSpSentinel) break;
             called += q.w & 0xffffu; mod += q.w >> 16;
         }
         FreqRecDev o;

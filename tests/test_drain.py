@@ -12,9 +12,11 @@ def test_drains_plus_remainder_equal_one_finalize_emulated(emul_lib, config, lag
     check_drain_equals_finalize(emul_lib, config, lag=lag, contig_len=60000, coverage=2.0)
 
 
-def test_drain_leaves_sparse_runs_to_finalize_emulated(emul_lib):
-    """--insertions: the side buffer is not partitioned by position, so nothing leaves early and nothing is lost"""
-    check_drain_equals_finalize(emul_lib, 3, expect_early=False, contig_len=40000, coverage=2.0)
+@pytest.mark.parametrize("config", [3, 6])
+def test_drain_with_side_buffer_records_emulated(emul_lib, config):
+    """--insertions / '.' blocks with haplotypes: the side-buffer records below the watermark are sorted, reduced and merged
+    into the drained rows while later batches may still be appending (their records read as sentinels until written)"""
+    check_drain_equals_finalize(emul_lib, config, contig_len=40000, coverage=2.0)
 
 
 def test_drain_order_violation_emulated(emul_lib):
@@ -34,8 +36,9 @@ def test_drains_plus_remainder_equal_one_finalize(cuda_lib, config, lag, chunks)
 
 
 @pytest.mark.gpu
-def test_drain_leaves_sparse_runs_to_finalize(cuda_lib):
-    check_drain_equals_finalize(cuda_lib, 3, expect_early=False, contig_len=400000, coverage=2.0)
+@pytest.mark.parametrize("config,lag", [(3, 1), (3, 2), (6, 1)])
+def test_drain_with_side_buffer_records(cuda_lib, config, lag):
+    check_drain_equals_finalize(cuda_lib, config, lag=lag, chunks=8, contig_len=400000, coverage=2.0)
 
 
 @pytest.mark.gpu
