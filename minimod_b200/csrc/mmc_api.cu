@@ -41,6 +41,7 @@ namespace {
 constexpr size_t kSlack = 64;                 // readable bytes after the last slice of a pool
 constexpr uint32_t kTileCells = 32768;        // cells per finalize tile (256 KB: one CTA; the tile scan is a single CTA, so tiles are large)
 constexpr uint32_t kExcCap = 1u << 22;        // exception-run starts per contig
+static_assert(kTileCells % (8 * 32 * 32) == 0 && kTileCells / (8 * 32 * 32) <= 8, "k_emit_records: a lane owns at most 8 ballot words of its warp's slice");
 
 std::string g_create_error;
 
@@ -145,6 +146,7 @@ struct mmc_ctx {
     bool drain_violated = false;                                   // a batch uploaded after a drain starts before its watermark
     unsigned long long sparse_lo = 0;                              // side-buffer records with a major key below this were returned by a drain
     double host_upload_ms = 0, host_launch_ms = 0; bool trace_host = false;   // MMC_TRACE_CREATE: host time inside mmc_batch_submit
+    double host_sect_ms[4] = {0, 0, 0, 0};                         // launch_decode: side-buffer reserve, state reset + general-kernel scratch, pool, launches
     cudaEvent_t ev_reset = nullptr; bool reset_pending = false;    // mmc_freq_reset() clears on fin_stream; the next decode launches wait for it on the device
     std::vector<int32_t> reset_touch;                              // (source of its asynchronous copy)
     mmc_freq_rec_t *h_drain[2] = {nullptr, nullptr}; size_t h_drain_cap[2] = {0, 0}; int drain_flip = 0;   // pinned, alternating
@@ -461,7 +463,14 @@ int reserve_sparse(mmc_ctx *ctx, const Slot &s) {
 int launch_decode(mmc_ctx *ctx, Slot &s) {
     const mmc_batch_t &b = s.pub;
     const uint32_t n = s.n_reads_submitted;
+    auto tick = [&](int k, std::chrono::steady_clock::time_point &t) {            // MMC_TRACE_CREATE: host time per section
+        const auto now = std::chrono::steady_clock::now();
+        ctx->host_sect_ms[k] += std::chrono::duration<double, std::milli>(now - t).count();
+        t = now;
+    };
+    auto tsec = std::chrono::steady_clock::now();
     { int rc = reserve_sparse(ctx, s); if (rc != MMC_OK) return rc; }
+    tick(0, tsec);
     // reset the slot's device state: err = ~0, view_n = 0, work counters and deferred count = 0
     // layout: u64 [0] err, [1] view_n, [4] pool cursor; u32 [4] work counter of k_decode_warp, [5] reads it defers,
     // [6] work counter of k_decode, [7] reads the flat path defers, [10] tiles, [11] reads with '.' blocks
@@ -492,6 +501,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         }
     }
 
+    tick(1, tsec);
     DecodeParams P;
     memset(&P, 0, sizeof(P));
     uint8_t *d = s.d_arena;
@@ -534,6 +544,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
         F.defer_list = s.d_defer_flat; F.defer_n = st32 + 7;
     }
 
+    tick(2, tsec);
     CU(ctx, cudaEventRecord(s.ev_k0, s.stream));
     if (s.use_stream) {
         // k_flat_setup prepares every read (state + CIGAR table in HBM), k_decode_stream merges the calls
@@ -602,6 +613,7 @@ int launch_decode(mmc_ctx *ctx, Slot &s) {
     ctx->tm.batches += 1;
     ctx->tm.reads += n;
     s.in_flight = true; s.timed = true;
+    tick(3, tsec);
     return MMC_OK;
 }
 
@@ -858,6 +870,9 @@ void mmc_destroy(mmc_ctx *ctx) {
     if (getenv("MMC_TRACE_CREATE"))
         fprintf(stderr, "[mmc_destroy] host time inside mmc_batch_submit: %.1f ms enqueuing copies / unpack kernels + batch analysis, %.1f ms launching the decode stage (scratch growth included)\n",
                 ctx->host_upload_ms, ctx->host_launch_ms);
+    if (getenv("MMC_TRACE_CREATE"))
+        fprintf(stderr, "[mmc_destroy]   of the latter: side-buffer reserve %.1f ms, state reset + general-kernel scratch %.1f ms, scratch pool %.1f ms, kernel launches %.1f ms\n",
+                ctx->host_sect_ms[0], ctx->host_sect_ms[1], ctx->host_sect_ms[2], ctx->host_sect_ms[3]);
     cudaDeviceSynchronize();
     for (Slot &s : ctx->slots) {
         if (s.h_arena) cudaFreeHost(s.h_arena);
