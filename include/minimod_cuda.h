@@ -247,8 +247,10 @@ const char *mmc_code_name(const mmc_ctx *ctx, int32_t code);  /* mod_code string
  *      (tid,pos) in coordinate order (tid, then pos).  Returns the rows before that watermark that no earlier
  *      drain returned, in the order mmc_freq_finalize() uses; waits only for the batches that hold a read
  *      starting before the watermark.  The rows stay valid until the second-next drain/finalize/reset (two
- *      pinned buffers alternate).  Returns no rows (and moves nothing) while the side buffer holds records
- *      (--insertions, haplotypes >= dense_haps, code ids >= dense_codes): those runs finalize at the end.
+ *      pinned buffers alternate).  Rows leave up to one position below the watermark: a read that starts exactly
+ *      at it may still add a side-buffer record at the position before (a leading insertion), and the rows of
+ *      a position leave together.  Side-buffer records (--insertions, haplotypes >= dense_haps, code ids >=
+ *      dense_codes) below the watermark are sorted, reduced and merged into the drained rows like at the end.
  *      After drains, mmc_freq_finalize() returns the REMAINING rows: concatenated, the drains and the
  *      remainder are the single-call table.  Counts are never cleared by a drain, so a broken promise loses
  *      nothing: the library notices a later batch that starts before the watermark, mmc_freq_finalize() then
