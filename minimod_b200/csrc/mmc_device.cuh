@@ -1095,9 +1095,9 @@ __global__ void __launch_bounds__(256) k_emit_records(const __grid_constant__ Fi
     if (w1 > c1) w1 = c1;
     const uint32_t *mask = p.mask + (unsigned long long)blockIdx.x * (p.cells_per_tile / 32u) + warp * (per_warp / 32u);
     const uint32_t n_words = (uint32_t)((w1 - w0 + 31u) >> 5);
-    // every lane owns kWpl consecutive ballot words of the warp's slice (per_warp / 32 / 32 = 4 with 32 K-cell tiles): its rows
-    // start at the exclusive prefix of the lanes' (and, through shared memory, the warps') non-zero counts, and it walks the set
-    // bits of its own words -- no warp-wide loop over the words, all lanes busy
+    // sparse slice (CpG tables: less than one row per ballot word): every lane owns kWpl consecutive ballot words of the warp's
+    // slice (per_warp / 32 / 32 = 4 with 32 K-cell tiles), its rows start at the exclusive prefix of the lanes' (and, through
+    // shared memory, the warps') non-zero counts, and it walks the set bits of its own words -- no warp-wide loop, all lanes busy
     constexpr uint32_t kWplMax = 8;
     const uint32_t wpl = (per_warp / 32u + 31u) / 32u;
     uint32_t m[kWplMax], cnt = 0;
@@ -1112,13 +1112,48 @@ __global__ void __launch_bounds__(256) k_emit_records(const __grid_constant__ Fi
     for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += x; }
     if (lane == 31u) ws[warp] = incl;
     __syncthreads();
-    if (cnt == 0u) return;
-    uint32_t at = incl - cnt;
-    for (uint32_t w = 0; w < warp; ++w) at += ws[w];
+    const uint32_t wtot = ws[warp];
+    if (wtot == 0u) return;
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < warp; ++w) wbase += ws[w];
     FreqRecDev *out = reinterpret_cast<FreqRecDev *>(p.out) + p.tile_offset[blockIdx.x];
     const uint32_t spp = 2u * (uint32_t)p.n_code_slots * (uint32_t)p.n_hap_slots;   // slots per position
     const unsigned long long pos0 = w0 / spp;                                      // one 64-bit division per warp; the rest is 32-bit
     const uint32_t rem0 = (uint32_t)(w0 - pos0 * spp);
+    if (wtot > 3u * n_words) {
+        // dense slice (config 4: eight rows per ballot word): the warp takes one word at a time, a lane per cell, so that
+        // the 32 rows of a step are consecutive in memory (coalesced stores); the lane-per-word walk below would scatter them
+        const uint32_t lt = (1u << lane) - 1u;
+        uint32_t running = wbase;
+        for (uint32_t wb = 0; wb < n_words; wb += 32u) {
+            const uint32_t mword = wb + lane < n_words ? mask[wb + lane] : 0u;
+            uint32_t todo = __ballot_sync(0xffffffffu, mword != 0u);
+            while (todo) {
+                const uint32_t wi = (uint32_t)__ffs((int)todo) - 1u;
+                todo &= todo - 1u;
+                const uint32_t f = __shfl_sync(0xffffffffu, mword, (int)wi);
+                if ((f >> lane) & 1u) {
+                    const uint32_t local = (wb + wi) * 32u + lane, t = rem0 + local;
+                    const unsigned long long v = j.cells[w0 + local];
+                    const uint32_t dpos = t / spp;
+                    uint32_t slot = t - dpos * spp;
+                    const uint32_t hslot = slot % (uint32_t)p.n_hap_slots; slot /= (uint32_t)p.n_hap_slots;
+                    const uint32_t code = slot % (uint32_t)p.n_code_slots; slot /= (uint32_t)p.n_code_slots;
+                    FreqRecDev rec;
+                    rec.tid = j.tid; rec.pos = j.lo + (int32_t)(pos0 + dpos);
+                    rec.n_called = (uint32_t)v; rec.n_mod = (uint32_t)(v >> 32);
+                    rec.ins_offset = 0;
+                    rec.hap = p.haplotypes ? (int16_t)((int32_t)hslot - 1) : (int16_t)-1;
+                    rec.strand = (uint8_t)slot; rec.code = (uint8_t)code; rec.reserved = 0;
+                    out[running + (uint32_t)__popc(f & lt)] = rec;
+                }
+                running += (uint32_t)__popc(f);
+            }
+        }
+        return;
+    }
+    if (cnt == 0u) return;
+    uint32_t at = wbase + incl - cnt;
 #pragma unroll
     for (uint32_t k = 0; k < kWplMax; ++k) {
         uint32_t f = m[k];
