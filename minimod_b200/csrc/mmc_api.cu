@@ -668,6 +668,38 @@ int wait_slot(mmc_ctx *ctx, Slot &s) {
 
 }  // namespace
 
+// Every environment variable the library reads, in one place.  None of them changes a result: they pick between
+// implementations that the test-suite proves equivalent (so that every path can be exercised on every fixture and A/B-timed
+// on the GPU), override a transport form, or turn on a trace.
+//   MMC_DECODE_PATH = general | warp | split | stream     which decode kernels run (default: per batch, by the reads' shape)
+//   MMC_STREAM_MINB = 4|5|6|8, MMC_STREAM_SPLIT = -1|0|1, MMC_WARP_OCC = 1..4, MMC_WARP_ARENA = bytes, MMC_DECODE_THREADS   tuning
+//   MMC_TEST_SMALL_SMEM = 1                                tiny shared-memory caps: forces the global-scratch fallbacks
+//   MMC_SEQ_PACKING = 2|4, MMC_CIGAR_PACKING = 8|32        transport forms (override mmc_opts_t)
+//   MMC_SPARSE_DEVICE_MIN = n                              side-buffer passes on the device from n records (0: always)
+//   MMC_TRACE_CREATE, MMC_TRACE_FINALIZE                   timing traces on stderr (read where they are used)
+static void apply_env_overrides(mmc_ctx *ctx) {
+    if (const char *e = getenv("MMC_DECODE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kMaxThreads && v % 32 == 0) ctx->threads = v; }
+    if (const char *e = getenv("MMC_TEST_SMALL_SMEM")) {
+        if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
+    }
+    if (const char *e = getenv("MMC_DECODE_PATH")) {
+        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->split_path = 0; ctx->stream_path = 0; }
+        else if (!strcmp(e, "warp")) { ctx->split_path = 0; ctx->stream_path = 0; }
+        else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
+        else if (!strcmp(e, "stream")) ctx->stream_path = 2;          // always (default 1: per batch, by the reads' shape)
+    }
+    if (const char *e = getenv("MMC_STREAM_SPLIT")) { const int v = atoi(e); if (v >= -1 && v <= 1) ctx->s_split_mode = v; }
+    if (const char *e = getenv("MMC_STREAM_MINB")) { int v = atoi(e); if (v == 8 || v == 6 || v == 5 || v == 4) ctx->s_minb = v; }
+    if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }
+    if (const char *e = getenv("MMC_SEQ_PACKING")) { int v = atoi(e); if (v == 2 || v == 4) ctx->seq_packing = v; }
+    if (const char *e = getenv("MMC_CIGAR_PACKING")) { int v = atoi(e); if (v == 8 || v == 32) ctx->cigar_packing = v; }
+    if (const char *e = getenv("MMC_SPARSE_DEVICE_MIN")) ctx->sparse_dev_min = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp
+        long v = atol(e);
+        if (v >= (long)sizeof(WFixed) + 256 && v <= 28 * 1024) { ctx->wv_arena[ctx->w_minb] = (uint32_t)(v & ~15l); ctx->w_pinned = 1; }
+    }
+}
+
 // =========================================================================================
 // C ABI
 // =========================================================================================
@@ -707,29 +739,10 @@ int mmc_create(mmc_ctx **out, const mmc_opts_t *opts, int32_t n_contigs, const c
     if (o.dense_haps > 255) o.dense_haps = 255;
     ctx->mods.assign(opts->mods, opts->mods + opts->n_mods);
     o.mods = ctx->mods.data();
-    if (const char *e = getenv("MMC_DECODE_THREADS")) { int v = atoi(e); if (v >= 32 && v <= kMaxThreads && v % 32 == 0) ctx->threads = v; }
-    if (const char *e = getenv("MMC_TEST_SMALL_SMEM")) {     // test hook: force the global-scratch paths
-        if (atoi(e)) { ctx->cig_smem_cap = 16; ctx->bitmap_smem_words = 8; ctx->idx_smem_cap = 8; }
-    }
-    if (const char *e = getenv("MMC_DECODE_PATH")) {         // "general": CTA-per-read kernel only (test hook / A-B timing)
-        if (!strcmp(e, "general")) { ctx->warp_path = 0; ctx->split_path = 0; ctx->stream_path = 0; }
-        else if (!strcmp(e, "warp")) { ctx->split_path = 0; ctx->stream_path = 0; }
-        else if (!strcmp(e, "split")) { ctx->split_path = 1; ctx->stream_path = 0; }
-        else if (!strcmp(e, "stream")) ctx->stream_path = 2;          // always (default 1: per batch, by the reads' shape)
-    }
-    if (const char *e = getenv("MMC_STREAM_SPLIT")) { const int v = atoi(e); if (v >= -1 && v <= 1) ctx->s_split_mode = v; }   // test hook / A-B timing
-    if (const char *e = getenv("MMC_STREAM_MINB")) { int v = atoi(e); if (v == 8 || v == 6 || v == 5 || v == 4) ctx->s_minb = v; }   // tuning
     ctx->s_head = (uint32_t)std::min<int>(opts->n_mods, kWLutSlots) * 256u;
-    if (const char *e = getenv("MMC_WARP_OCC")) { int v = atoi(e); if (v >= 1 && v <= 4) { ctx->w_minb = v; ctx->w_pinned = 1; } }   // tuning
     ctx->seq_packing = opts->seq_packing == 2 ? 2 : 4;
-    if (const char *e = getenv("MMC_SEQ_PACKING")) { int v = atoi(e); if (v == 2 || v == 4) ctx->seq_packing = v; }   // test hook
     ctx->cigar_packing = opts->cigar_packing == 8 ? 8 : 32;
-    if (const char *e = getenv("MMC_CIGAR_PACKING")) { int v = atoi(e); if (v == 8 || v == 32) ctx->cigar_packing = v; }   // test hook
-    if (const char *e = getenv("MMC_SPARSE_DEVICE_MIN")) ctx->sparse_dev_min = strtoull(e, nullptr, 10);   // test hook: 0 = always sort sparse records on the device
-    if (const char *e = getenv("MMC_WARP_ARENA")) {          // bytes of shared memory per warp (test hook / tuning)
-        long v = atol(e);
-        if (v >= (long)sizeof(WFixed) + 256 && v <= 28 * 1024) { ctx->wv_arena[ctx->w_minb] = (uint32_t)(v & ~15l); ctx->w_pinned = 1; }
-    }
+    apply_env_overrides(ctx);
     for (int mb = 1; mb <= 4; ++mb) {                        // k_flat_setup holds WRead + the un-sampled CIGAR arrays of most reads
         const uint32_t flex = ctx->wv_arena[mb] - (uint32_t)sizeof(WFixed);
         ctx->wv_setup_arena[mb] = kWReadBytes + std::min<uint32_t>(std::max<uint32_t>(4608u, (flex / 2u) & ~15u), 24576u);
