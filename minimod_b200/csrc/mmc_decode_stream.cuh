@@ -18,8 +18,9 @@
 // prefix arrays, so 28-32 warps are resident per SM whatever the read length (k_decode_warp: 24 on 15 kb reads,
 // 8 on 50 kb reads), and the per-read index build (23 % of k_decode_warp's instructions) is gone.
 //
-// Per-read hand-over (WRead + dir|cq|cr written by k_flat_setup) is double-buffered with cp.async.bulk +
-// mbarrier: the next read's record is in flight while the current one is decoded.
+// The SEQ ring is fed by cp.async.bulk + mbarrier (s_prefetch): the 32 vectors of the next count step are in flight while
+// the current round of calls is decoded.  The per-read record (WRead, ~0.4 KB) is copied by the lanes; the CIGAR table stays
+// where k_flat_setup wrote it and is looked up in place.
 #ifndef MMC_DECODE_STREAM_CUH
 #define MMC_DECODE_STREAM_CUH
 
@@ -264,12 +265,6 @@ __device__ __noinline__ void s_select_tile(const DecodeParams &P, uint32_t aoff,
     __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------
-// phase B of a text tile, common case: read positions T->rank[0..n) -> reference positions -> context -> threshold ->
-// dense cells.  `freq`, one requested code per block (K == 1), canonical base A/C/G/T (w_fast_ok).
-//   C0  class A (bit 31 of the position: the read base is not literally 'A')
-//   EX  any of: --insertions, --haplotypes, sampled CIGAR (kept out of the lean instantiation)
-// ---------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------
 // phase B of a text tile, common case: read positions T->rank[0..n) -> reference positions -> context -> threshold ->
 // dense cells.  `freq`, one requested code per block (K == 1), canonical base A/C/G/T (w_fast_ok).
