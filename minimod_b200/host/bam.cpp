@@ -135,7 +135,7 @@ long BgzfReader::read(void *buf, size_t n) {
         }
         if (s->bad) return -1;
         const size_t take = std::min(n - done, s->out_len - cur_off_);
-        memcpy(p + done, s->out.data() + cur_off_, take);
+        if (p) memcpy(p + done, s->out.data() + cur_off_, take);
         done += take; cur_off_ += take;
         if (cur_off_ == s->out_len) {
             { std::lock_guard<std::mutex> lk(mu_); s->st = EMPTY; ++consumed_; }
@@ -150,6 +150,17 @@ BamFile::~BamFile() { if (gz_) gzclose(gz_); delete bgzf_; }
 
 long BamFile::read_some(void *buf, size_t n) {
     if (bgzf_) return bgzf_->read(buf, n);
+    if (!buf) {                                                   // skip (plain gzip stream): through a scratch buffer
+        std::vector<uint8_t> scratch(std::min<size_t>(n, 1u << 16));
+        size_t left = n;
+        while (left) {
+            const long got = read_some(scratch.data(), std::min(left, scratch.size()));
+            if (got < 0) return -1;
+            if (got == 0) break;
+            left -= (size_t)got;
+        }
+        return (long)(n - left);
+    }
     size_t done = 0;
     uint8_t *p = (uint8_t *)buf;
     while (done < n) {
@@ -216,7 +227,7 @@ static void restore_long_cigar(BamRecord *r) {
     d.insert(d.end(), r->seq(), tag0);                                    // seq, qual, aux before CG
     d.insert(d.end(), tag1, end);                                         // aux after CG
     r->n_cigar = n;
-    r->l_data = (int32_t)d.size();
+    r->l_data = (int32_t)(d.size() + (r->no_qual ? (size_t)r->l_qseq : 0));   // as if QUAL were there: the length htslib's record has
     d.resize(d.size() + 8, 0);
     r->data.swap(d);
 }
@@ -233,11 +244,17 @@ int BamFile::next(BamRecord *r) {
     r->n_cigar = le16(fx + 12); r->flag = le16(fx + 14);
     r->l_qseq = (int32_t)le32(fx + 16);
     r->l_data = (int32_t)(block - 32);
-    r->data.resize((size_t)r->l_data + 8);
-    if (r->l_data && !read_exact(r->data.data(), (size_t)r->l_data)) return -1;
-    memset(r->data.data() + r->l_data, 0, 8);
-    size_t fixed = (size_t)r->l_qname + 4 * (size_t)r->n_cigar + ((size_t)(r->l_qseq < 0 ? 0 : r->l_qseq) + 1) / 2 + (size_t)(r->l_qseq < 0 ? 0 : r->l_qseq);
+    const size_t lq = (size_t)(r->l_qseq < 0 ? 0 : r->l_qseq);
+    const size_t head = (size_t)r->l_qname + 4 * (size_t)r->n_cigar + (lq + 1) / 2, fixed = head + lq;
     if (r->l_qseq < 0 || fixed > (size_t)r->l_data) return -1;
+    // qname | cigar | seq, then QUAL is skipped (never copied out of the inflated block), then the aux fields
+    r->no_qual = true;
+    const size_t kept = (size_t)r->l_data - lq;
+    r->data.resize(kept + 8);
+    if (head && !read_exact(r->data.data(), head)) return -1;
+    if (lq && read_some(nullptr, lq) != (long)lq) return -1;
+    if (kept > head && !read_exact(r->data.data() + head, kept - head)) return -1;
+    memset(r->data.data() + kept, 0, 8);
     restore_long_cigar(r);
     return 1;
 }

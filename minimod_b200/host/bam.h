@@ -27,13 +27,14 @@ struct BamRecord {
     int32_t l_qseq = 0;
     uint8_t l_qname = 0;
     int32_t l_data = 0;                 // block_size - 32, what load_db() budgets with (-B)
-    std::vector<uint8_t> data;          // qname, cigar, seq, qual, aux
+    bool no_qual = false;               // QUAL is not in `data` (BamFile::next() skips it: two thirds of a record nobody here reads)
+    std::vector<uint8_t> data;          // qname, cigar, seq, [qual,] aux
 
     const char *qname() const { return (const char *)data.data(); }
     const uint8_t *cigar() const { return data.data() + l_qname; }                    // unaligned u32 LE
     const uint8_t *seq() const { return cigar() + 4 * (size_t)n_cigar; }
-    const uint8_t *aux() const { return seq() + ((size_t)l_qseq + 1) / 2 + (size_t)l_qseq; }
-    const uint8_t *end() const { return data.data() + l_data; }
+    const uint8_t *aux() const { return seq() + ((size_t)l_qseq + 1) / 2 + (no_qual ? 0 : (size_t)l_qseq); }
+    const uint8_t *end() const { return data.data() + l_data - (no_qual ? l_qseq : 0); }
     // first aux field with this tag: pointer to its type byte, or nullptr (bam_aux_get)
     const uint8_t *aux_get(const char tag[2]) const;
 };
@@ -45,7 +46,7 @@ public:
     ~BgzfReader();
     static bool is_bgzf(const std::string &path);
     bool open(const std::string &path, int threads);
-    long read(void *buf, size_t n);              // bytes delivered (< n only at EOF), -1 on a corrupt block
+    long read(void *buf, size_t n);              // bytes delivered (< n only at EOF), -1 on a corrupt block; buf == nullptr: skipped, not copied
 private:
     enum State { EMPTY, FILLED, BUSY, DONE };
     struct Slot { std::vector<uint8_t> in, out; size_t out_len = 0; State st = EMPTY; bool bad = false; };
