@@ -23,8 +23,13 @@ except Exception:
 def test_full_size_table_equals_the_reference(config):
     if config not in SUMS:
         pytest.skip("no reference digest committed for this config (tools/make_fullsize_checksums.py)")
-    if os.environ.get("MINIMOD_FULLSIZE", "1") == "0":
+    mode = os.environ.get("MINIMOD_FULLSIZE", "1")
+    if mode == "0":
         pytest.skip("MINIMOD_FULLSIZE=0")
+    if config == 4 and mode != "all":
+        # 202 M rows: ~2 minutes and ~12 GB of host memory for the text.  Run with MINIMOD_FULLSIZE=all (tools/gpu_final.sh does;
+        # profiles/r02c_pytest_gpu.log is such a run: 200 passed with all four configs)
+        pytest.skip("config 4 at full size needs MINIMOD_FULLSIZE=all")
     want = SUMS[config]
     td = tempfile.mkdtemp(prefix="mm_full_")
     try:
