@@ -156,6 +156,29 @@ def b_long_read(bp):
 
 LONG_REF = "".join(random.Random(5).choice("ACGT") for _ in range(90000))
 
+
+def b_cigar_len_boundaries(bp):
+    """Op lengths on the boundaries of the CIGAR byte form (include/minimod_cuda.h): 14 | 15 (first escape list) ... 269 | 270
+    (second list), in every op kind, more than 32 ops per read so that the ranks into the escape lists carry over steps."""
+    lens = [14, 15, 16, 1, 269, 270, 271, 2, 15, 255, 256, 14, 270, 3, 269, 15]
+    ops, q, r = [], 0, 0
+    for rep in range(3):
+        for k, n in enumerate(lens):
+            ops.append(f"{n}M"); q += n; r += n
+            kind = "IDN"[(k + rep) % 3]
+            m = lens[(k * 7 + rep) % len(lens)]
+            ops.append(f"{m}{kind}")
+            if kind == "I":
+                q += m
+            else:
+                r += m
+    seq = "".join(random.Random(11).choice("ACGT") for _ in range(q))
+    assert r + 2000 < len(LONG_REF)
+    for rev in (False, True):
+        for status in ("?", "."):
+            mm, cnt = mm_for(seq, "C", "m", status, 2, rev)
+            add_read(bp, 1, 2000, 16 if rev else 0, seq, "".join(ops), mm, ml_bytes(cnt, 13))
+
 def b_huge_ops(bp):
     """CIGAR lengths >= 2^26: the warp kernels' plain prefix scans leave such reads to k_decode (saturating scans).
     Forward strand only: a CIGAR longer than the read on a reverse read is fatal in the reference (its reversed walk starts
@@ -195,6 +218,8 @@ CASES = [
     case("long_read_insertions", b_long_read, contigs="long", codes="m[C]", insertions=True),
     case("wild_dense_codes_overflow", b_lower_and_chebi, codes="*", opts=dict(dense_codes=1)),
     case("huge_cigar_ops", b_huge_ops),
+    case("cigar_len_boundaries", b_cigar_len_boundaries, contigs="long", codes="m[*]"),
+    case("cigar_len_boundaries_insertions", b_cigar_len_boundaries, contigs="long", codes="m[C]", insertions=True),
     case("no_reads", lambda bp: None),
 ]
 
